@@ -1,0 +1,330 @@
+// Ray / primitive intersection and the reference-exact ("literal") traversal.
+//
+// Replaces (reference file:line, /root/reference/src/rayTracerDistAccelShdPhtnMap/):
+//   myRay.java:91-102            getTransformedRay (in-place normalisation of the source ray)
+//   myGeomBase.java:132-162      myBBox.intersectCheck, "entry t > 0" rule
+//   myPlanarObject.java:104-115,165-211  plane hit + inside test, stateless two-sidedness
+//   myImpObject.java:76-94,174-192,259-302  sphere / open cylinder / capped cylinder
+//   myScene.java:879-903         calcShadow / findClosestRayHit over the top-level list
+//   myGeomBase.java:216-222,268-302,397-421  root gate, list loops, ordered BVH recursion
+//   mySceneObject.java:33-38,117-127  shadow rule, instance forwarding (SURVEY Q7,Q8)
+#pragma once
+#include "dev_math.cuh"
+
+namespace drt {
+
+// origin, "direction" vector (may be re-normalised in place), "dirAra" copy (never re-normalised) -- myRay.java:14-18
+struct Ray { D3 o, d, a; bool norm; };
+
+struct Hit {
+  double t;
+  int32_t prim, arg0, arg1, state;        // state: polygon winding state used (0/1[/2 for planes])
+  int32_t hitXform, shaderOverride, inst;
+  D3 loc;                                  // hit point in the primitive's space (rayHit.hitLoc)
+  D3 rawDir;                               // rayHit.fwdTransRayDir
+};
+__device__ __forceinline__ void hitReset(Hit& h) { h.t = DRT_DMAX; h.prim = -1; h.arg0 = 0; h.arg1 = 0; h.state = 0; h.hitXform = -1; h.shaderOverride = -1; h.inst = -1; }
+
+struct TraceCounters { unsigned long long box, prim; };
+
+__device__ __forceinline__ Ray makeRay(D3 o, D3 dirNormalized) { Ray r; r.o = o; r.d = dirNormalized; r.a = dirNormalized; r.norm = true; return r; }
+// getTransformedRay: normalise the source direction in place (only if it is not already unit length: canonical mode,
+// see DESIGN.md "re-normalisation"), transform origin as a point and direction as a vector, do NOT normalise the result.
+__device__ __forceinline__ Ray xfRay(Ray& src, const double* __restrict__ inv) {
+  if (!src.norm) { src.d = norm3(src.d); src.norm = true; }
+  Ray r; r.o = xfPoint(inv, src.o); r.d = xfVector(inv, src.d); r.a = r.d; r.norm = false; return r;
+}
+__device__ __forceinline__ D3 pointOnRay(const Ray& r, double t) { return d3((r.d.x * t) + r.o.x, (r.d.y * t) + r.o.y, (r.d.z * t) + r.o.z); }
+
+// ---- slab test, literal (true divisions, running min/max that NaN never replaces)
+__device__ __forceinline__ bool boxTest(const double* __restrict__ mn, const double* __restrict__ mx, const Ray& r, double& tEntry, int& face) {
+  double o[3] = {r.o.x, r.o.y, r.o.z}, d[3] = {r.a.x, r.a.y, r.a.z};
+  double tMin[3], tMax[3], biggestMin = -DRT_DMAX; int idx = -1;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double v1 = (mn[i] - o[i]) / d[i], v2 = (mx[i] - o[i]) / d[i];
+    if (v1 < v2) { tMin[i] = v1; tMax[i] = v2; if (biggestMin < v1) { idx = i; biggestMin = v1; } }
+    else { tMin[i] = v2; tMax[i] = v1; if (biggestMin < v2) { idx = i + 3; biggestMin = v2; } }
+  }
+  double minMax = DRT_DMAX, maxMin = -DRT_DMAX;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { if (tMax[i] < minMax) minMax = tMax[i]; if (tMin[i] > maxMin) maxMin = tMin[i]; }
+  if ((minMax > maxMin) && biggestMin > 0) { tEntry = biggestMin; face = idx; return true; }
+  return false;
+}
+
+// ---- primitives. `r` is the ray in the primitive's space, rawDir the direction recorded in the hit.
+// Returns true and fills h (t, loc, args, state) on a hit. time: ray time for moving spheres.
+__device__ __noinline__ bool primTest(const DScene& S, int primIdx, const Ray& r, D3 rawDir, double time, Hit& h) {
+  const FPrim P = S.prims[primIdx];
+  const double* __restrict__ q = S.pdata + P.data;
+  switch (P.type) {
+    case PT_SPHERE: case PT_MOVSPHERE: {
+      D3 c = d3(q[0], q[1], q[2]); double rx = q[3], ry = q[4], rz = q[5];
+      if (P.type == PT_MOVSPHERE) { D3 bMa = d3(q[6] - c.x, q[7] - c.y, q[8] - c.z); c = d3(c.x + time * bMa.x, c.y + time * bMa.y, c.z + time * bMa.z); }
+      double dxr = r.d.x / rx, dyr = r.d.y / ry, dzr = r.d.z / rz;
+      double a = ((dxr) * (dxr)) + ((dyr) * (dyr)) + ((dzr) * (dzr));
+      D3 pC = d3((r.o.x - c.x) / rx, (r.o.y - c.y) / ry, (r.o.z - c.z) / rz);
+      double b = 2 * (((dxr) * pC.x) + ((dyr) * pC.y) + ((dzr) * pC.z));
+      double cc = (pC.x * pC.x) + (pC.y * pC.y) + (pC.z * pC.z) - 1;
+      double ta = 2 * a, discr = ((b * b) - (2 * ta * cc));
+      if (!(discr < 0)) {
+        double d1 = sqrt(discr), t1 = (-1 * b + d1) / (ta), t2 = (-1 * b - d1) / (ta);
+        double tv = jminD(t1, t2);
+        if (tv < DRT_EPS) { tv = jmaxD(t1, t2); if (tv < DRT_EPS) return false; }
+        h.t = tv; h.loc = pointOnRay(r, tv); h.prim = primIdx; h.arg0 = 0; h.arg1 = 0; h.state = 0; h.rawDir = rawDir; return true;
+      }
+      return false;
+    }
+    case PT_TRI: case PT_QUAD: {
+      const int n = (P.type == PT_TRI) ? 3 : 4, stride = (P.type == PT_TRI) ? DRT_TRI_STATE : DRT_QUAD_STATE;
+      int st = 0; const double* __restrict__ s = q;
+      D3 N = d3(s[3 * n], s[3 * n + 1], s[3 * n + 2]);
+      double planeRes = dot3(N, r.d);
+      if (!(fabs(planeRes) > 0)) return false;
+      if (planeRes > 0) {                       // invertNormal(): continue with the reversed winding
+        st = 1; s = q + stride; N = d3(s[3 * n], s[3 * n + 1], s[3 * n + 2]); planeRes = dot3(N, r.d);
+        if (!(fabs(planeRes) > 0) || planeRes > 0) return false;
+      }
+      double t = -(dot3(N, r.o) + s[3 * n + 3]) / planeRes;
+      if (!(t > DRT_EPS)) return false;
+      D3 p = pointOnRay(r, t);
+#pragma unroll 1
+      for (int i = 0; i < n; ++i) {
+        int pi = (i == 0 ? n - 1 : i - 1);
+        D3 vi = d3(s[3 * i], s[3 * i + 1], s[3 * i + 2]), vp = d3(s[3 * pi], s[3 * pi + 1], s[3 * pi + 2]);
+        D3 ir = d3(p.x - vi.x, p.y - vi.y, p.z - vi.z), e = d3(vi.x - vp.x, vi.y - vp.y, vi.z - vp.z);
+        D3 tmp = cross3(ir, e);
+        if (dot3(tmp, N) < -DRT_EPS) return false;
+      }
+      h.t = t; h.loc = p; h.prim = primIdx; h.arg0 = 0; h.arg1 = 0; h.state = st; h.rawDir = rawDir; return true;
+    }
+    case PT_PLANE: {
+      int st = 0; D3 N = d3(q[0], q[1], q[2]); double D = q[3];
+      double planeRes = dot3(N, r.d);
+      if (!(fabs(planeRes) > 0)) return false;
+      if (planeRes > 0) { st = 1; N = d3(q[4], q[5], q[6]); D = q[7]; planeRes = dot3(N, r.d); if (!(fabs(planeRes) > 0)) return false;
+        if (planeRes > 0) { st = 2; N = d3(q[8], q[9], q[10]); D = q[11]; planeRes = dot3(N, r.d); if (!(fabs(planeRes) > 0) || planeRes > 0) return false; } }
+      double t = -(dot3(N, r.o) + D) / planeRes;
+      if (!(t > DRT_EPS)) return false;
+      h.t = t; h.loc = pointOnRay(r, t); h.prim = primIdx; h.arg0 = 0; h.arg1 = 0; h.state = st; h.rawDir = rawDir; return true;
+    }
+    case PT_HCYL: {
+      double cx = q[0], cz = q[2], radX = q[3], radZ = q[4], yTop = q[5], yBot = q[6];
+      double dxr = r.d.x / radX, dzr = r.d.z / radZ, pcx = (r.o.x - cx) / radX, pcz = (r.o.z - cz) / radZ;
+      double a = ((dxr) * (dxr)) + ((dzr) * (dzr)), b = 2 * (((dxr) * pcx) + ((dzr) * pcz)), c = (pcx * pcx) + (pcz * pcz) - 1;
+      double discr = ((b * b) - (4 * a * c));
+      if (!(discr < 0)) {
+        double d1 = sqrt(discr), t1 = (-b + d1) / (2 * a), t2 = (-b - d1) / (2 * a);
+        double tv = jminD(t1, t2), to = jmaxD(t1, t2);
+        if (tv < -DRT_EPS) { double tmp = to; to = tv; tv = tmp; if (tv < -DRT_EPS) return false; }
+        double y1 = r.o.y + (tv * r.d.y);
+        if ((tv > DRT_EPS) && (y1 > yBot) && (y1 < yTop)) { h.t = tv; h.loc = pointOnRay(r, tv); h.prim = primIdx; h.arg0 = 0; h.arg1 = 0; h.state = 0; h.rawDir = rawDir; return true; }
+        double y2 = r.o.y + (to * r.d.y);
+        if ((to > DRT_EPS) && (y2 > yBot) && (y2 < yTop)) { h.t = to; h.loc = pointOnRay(r, to); h.prim = primIdx; h.arg0 = 1; h.arg1 = 0; h.state = 0; h.rawDir = rawDir; return true; }
+      }
+      return false;
+    }
+    case PT_CYL: {
+      double cx = q[0], cz = q[2], radX = q[3], radZ = q[4], yTop = q[5], yBot = q[6];
+      double dxr = r.d.x / radX, dzr = r.d.z / radZ, pcx = (r.o.x - cx) / radX, pcz = (r.o.z - cz) / radZ;
+      double a = ((dxr) * (dxr)) + ((dzr) * (dzr)), b = 2 * (((dxr) * pcx) + ((dzr) * pcz)), c = (pcx * pcx) + (pcz * pcz) - 1;
+      double discr = ((b * b) - (4 * a * c));
+      if (!(discr < 0)) {
+        double d1 = sqrt(discr), t1 = (-b + d1) / (2 * a), t2 = (-b - d1) / (2 * a);
+        double cv = jminD(t1, t2), co = jmaxD(t1, t2);
+        if (cv < DRT_EPS) { co = cv; cv = jmaxD(t1, t2); if (cv < DRT_EPS) return false; }
+        bool planeRes = true; double pl[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double* e = q + 7 + 4 * i;
+          double den = e[0] * r.d.x + e[1] * r.d.y + e[2] * r.d.z;
+          if (fabs(den) > DRT_EPS) { double num = e[0] * r.o.x + e[1] * r.o.y + e[2] * r.o.z + e[3]; pl[i] = -num / den; } else pl[i] = 10000;
+        }
+        double pv = jminD(pl[0], pl[1]); int vis = (pv == pl[0] ? 0 : 1);
+        if (pv < 0) { pv = pl[vis]; if (pv < DRT_EPS) planeRes = false; }
+        double tv, mxC = jmaxD(cv, co), mnC = jminD(cv, co);
+        if (planeRes && (((mnC <= 0) && (pv >= -DRT_EPS) && (pv <= mxC)) || ((pv > mnC) && (pv <= mxC)))) tv = pv; else { tv = cv; vis = 2; }
+        double y1 = r.o.y + (tv * r.d.y);
+        if ((y1 + DRT_EPS >= yBot) && (y1 - DRT_EPS <= yTop)) { h.t = tv; h.loc = pointOnRay(r, tv); h.prim = primIdx; h.arg0 = vis; h.arg1 = 0; h.state = 0; h.rawDir = rawDir; return true; }
+      }
+      return false;
+    }
+    case PT_BOX: {
+      double t; int face; if (!boxTest(q, q + 3, r, t, face)) return false;
+      // rendered box: ray direction recorded in the hit is CTM x transformed direction (myGeomBase.java:160)
+      h.t = t; h.loc = pointOnRay(r, t); h.prim = primIdx; h.arg0 = 0; h.arg1 = face; h.state = 0;
+      h.rawDir = xfVector(S.xforms[P.xform].m, r.d); return true;
+    }
+  }
+  return false;
+}
+
+#define DRT_STACK 48
+struct Frame { int32_t node; double tL; };     // node >= 0: "after left" of that node; node == -1: "after right", tL saved
+
+template <int LVL> struct Lvl {};
+
+// ---------------------------------------------------------------------------------------------------------------
+// closest hit
+// ---------------------------------------------------------------------------------------------------------------
+template <int LVL>
+__device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc);
+
+// myGeomList.traverseStruct: every child gets a fresh transform of `_ray`; first strictly smaller t wins;
+// the winner's CTM becomes list.CTM x child.CTM (child.hitXform).
+template <int LVL>
+__device__ __forceinline__ double leafClosest(const DScene& S, int listIdx, Ray& _ray, double time, Hit& res, TraceCounters* tc) {
+  const FList L = S.lists[listIdx];
+  double clsT = DRT_DMAX;
+  for (int i = 0; i < L.childCount; ++i) {
+    const FObjRef c = S.children[L.childStart + i];
+    Ray r = xfRay(_ray, S.xforms[c.xform].inv);
+    Hit h; hitReset(h); bool got = false;
+    if (c.kind == OK_PRIM) { if (tc) ++tc->prim; got = primTest(S, c.idx, r, _ray.d, time, h); }
+    else {   // instance: the already transformed ray is forwarded as both rays (mySceneObject.java:123-127)
+      const FInstance I = S.instances[c.idx];
+      if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; got = primTest(S, I.baseIdx, r, r.d, time, h); }
+      else if (LVL == 1) got = accelClosest<2>(S, I.baseKind, I.baseIdx, r, r, time, h, tc);
+      if (got) { if (I.shader >= 0) h.shaderOverride = I.shader; if (h.inst < 0) h.inst = I.serial; }
+    }
+    if (got && h.t < clsT) { clsT = h.t; res = h; res.hitXform = c.hitXform; }
+  }
+  return clsT;
+}
+
+// myAccelStruct.intersectCheck (root gate) + myBVH.traverseStruct, iteratively.
+// Semantics of the recursion kept exactly: left subtree first; right subtree only if its box is hit and
+// (left found nothing or right-entry t < left result t); result = left if left.t <= right.t.  Because every level
+// combines with "min, left wins ties", the overall winner is the DFS-first minimum over all visited leaves; the
+// per-subtree minima needed for the pruning decisions live on an explicit frame stack.
+template <int LVL>
+__device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc) {
+  double te; int face;
+  if (kind == OK_LIST) {
+    const FList& L = S.lists[idx];
+    if (tc) ++tc->box;
+    if (!boxTest(L.bmin, L.bmax, trans, te, face)) return false;
+    Hit h; hitReset(h); double t = leafClosest<LVL>(S, idx, _ray, time, h, tc);
+    if (t < DRT_DMAX) { out = h; return true; }
+    return false;
+  }
+  const FBvh& B = S.bvhs[idx];
+  if (tc) ++tc->box;
+  if (!boxTest(B.bmin, B.bmax, trans, te, face)) return false;
+  Hit best; hitReset(best);
+  Frame stack[DRT_STACK]; int sp = 0;
+  int32_t node = B.root; double tCur = DRT_DMAX;
+  while (true) {
+    bool ret = false;
+    int32_t afterLeftOf = -1;
+    if (node < 0) {                    // leaf
+      Hit h; hitReset(h); tCur = leafClosest<LVL>(S, ~node, _ray, time, h, tc);
+      if (h.t < best.t) best = h;
+      ret = true;
+    } else {
+      const FNode& N = S.nodes[node];
+      if (tc) ++tc->box;
+      if (boxTest(N.lmin, N.lmax, trans, te, face) && sp < DRT_STACK) { stack[sp].node = node; stack[sp].tL = 0; ++sp; node = N.left; tCur = DRT_DMAX; continue; }
+      tCur = DRT_DMAX; afterLeftOf = node;
+    }
+    while (true) {
+      if (afterLeftOf >= 0) {          // left subtree of `afterLeftOf` finished with tCur
+        const FNode& N = S.nodes[afterLeftOf];
+        if (tc) ++tc->box;
+        bool hr = boxTest(N.rmin, N.rmax, trans, te, face);
+        if (hr && (!(tCur < DRT_DMAX) || te < tCur) && sp < DRT_STACK) { stack[sp].node = -1; stack[sp].tL = tCur; ++sp; node = N.right; tCur = DRT_DMAX; ret = false; break; }
+        afterLeftOf = -1; ret = true;  // result of this node = tL (an untraversed right box can never win: te >= tL)
+      }
+      if (ret) {
+        if (sp == 0) { if (best.t < DRT_DMAX) { out = best; return true; } return false; }
+        --sp;
+        if (stack[sp].node >= 0) { afterLeftOf = stack[sp].node; continue; }
+        double tL = stack[sp].tL; tCur = (tL <= tCur) ? tL : tCur;       // min, left wins ties
+        continue;
+      }
+    }
+  }
+}
+
+// myScene.findClosestRayHit: linear scan of the top-level list, first-inserted wins among equal t
+__device__ __forceinline__ bool closestHit(const DScene& S, Ray& ray, double time, Hit& best, TraceCounters* tc) {
+  hitReset(best);
+  for (int i = 0; i < S.g.numTop; ++i) {
+    const FObjRef o = S.top[i];
+    Ray tr = xfRay(ray, S.xforms[o.xform].inv);
+    Hit h; hitReset(h); bool got = false;
+    if (o.kind == OK_PRIM) { if (tc) ++tc->prim; got = primTest(S, o.idx, tr, ray.d, time, h); if (got) h.hitXform = o.xform; }
+    else if (o.kind == OK_INSTANCE) {
+      const FInstance I = S.instances[o.idx];
+      if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; got = primTest(S, I.baseIdx, tr, tr.d, time, h); if (got) h.hitXform = o.xform; }
+      else got = accelClosest<1>(S, I.baseKind, I.baseIdx, tr, tr, time, h, tc);
+      if (got) { if (I.shader >= 0) h.shaderOverride = I.shader; if (h.inst < 0) h.inst = I.serial; }
+    } else got = accelClosest<1>(S, o.kind, o.idx, ray, tr, time, h, tc);
+    if (got && h.t < best.t) best = h;
+  }
+  return best.t < DRT_DMAX;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// any hit (shadow rays): hit AND (distToLight - t) > eps.  The BVH form never tests its root box; every list
+// (top-level or BVH leaf) gates on its own box with the same rule.
+// ---------------------------------------------------------------------------------------------------------------
+template <int LVL>
+__device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc);
+
+template <int LVL>
+__device__ __forceinline__ bool listShadow(const DScene& S, int listIdx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc) {
+  const FList L = S.lists[listIdx];
+  double te; int face;
+  if (tc) ++tc->box;
+  if (!(boxTest(L.bmin, L.bmax, trans, te, face) && (dist - te) > DRT_EPS)) return false;
+  for (int i = 0; i < L.childCount; ++i) {
+    const FObjRef c = S.children[L.childStart + i];
+    Ray r = xfRay(_ray, S.xforms[c.xform].inv);
+    Hit h; hitReset(h);
+    if (c.kind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, c.idx, r, _ray.d, time, h) && (dist - h.t) > DRT_EPS) return true; }
+    else {
+      const FInstance I = S.instances[c.idx];
+      if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, I.baseIdx, r, r.d, time, h) && (dist - h.t) > DRT_EPS) return true; }
+      else if (LVL == 1) { if (accelShadow<2>(S, I.baseKind, I.baseIdx, r, r, time, dist, tc)) return true; }
+    }
+  }
+  return false;
+}
+template <int LVL>
+__device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc) {
+  if (kind == OK_LIST) return listShadow<LVL>(S, idx, _ray, trans, time, dist, tc);
+  const FBvh& B = S.bvhs[idx];
+  int32_t stack[DRT_STACK]; int sp = 0; int32_t node = B.root;
+  double te; int face;
+  while (true) {
+    if (node < 0) { if (listShadow<LVL>(S, ~node, _ray, trans, time, dist, tc)) return true; }
+    else {
+      const FNode& N = S.nodes[node];
+      if (tc) tc->box += 2;
+      bool hl = boxTest(N.lmin, N.lmax, trans, te, face) && (dist - te) > DRT_EPS;
+      bool hr = boxTest(N.rmin, N.rmax, trans, te, face) && (dist - te) > DRT_EPS;
+      if (hl) { if (hr && sp < DRT_STACK) stack[sp++] = N.right; node = N.left; continue; }
+      if (hr) { node = N.right; continue; }
+    }
+    if (sp == 0) return false;
+    node = stack[--sp];
+  }
+}
+__device__ __forceinline__ bool anyHit(const DScene& S, Ray& ray, double time, double dist, TraceCounters* tc) {
+  for (int i = 0; i < S.g.numTop; ++i) {
+    const FObjRef o = S.top[i];
+    Ray tr = xfRay(ray, S.xforms[o.xform].inv);
+    Hit h; hitReset(h);
+    if (o.kind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, o.idx, tr, ray.d, time, h) && (dist - h.t) > DRT_EPS) return true; }
+    else if (o.kind == OK_INSTANCE) {
+      const FInstance I = S.instances[o.idx];
+      if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, I.baseIdx, tr, tr.d, time, h) && (dist - h.t) > DRT_EPS) return true; }
+      else if (accelShadow<1>(S, I.baseKind, I.baseIdx, tr, tr, time, dist, tc)) return true;
+    } else if (accelShadow<1>(S, o.kind, o.idx, ray, tr, time, dist, tc)) return true;
+  }
+  return false;
+}
+
+}  // namespace drt

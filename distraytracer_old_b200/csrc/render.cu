@@ -1,0 +1,466 @@
+// Wavefront renderer for sm_100a: ray generation, closest-hit trace, surface shading with secondary-ray enqueue
+// (warp-aggregated atomic compaction), light/shadow pass, bottom-up bounce resolve, pixel resolve.
+//
+// Replaces the reference's recursive per-pixel loop (reference file:line, /root/reference/src/rayTracerDistAccelShdPhtnMap/):
+//   k_raygen   myScene.java:1447-1462 (jittered AA), :1386-1406 + :868-875 (depth of field), :1563-1585 (fisheye), :1687-1701 (ortho),
+//              single-sample loops :1498-1508, :1606-1625, :1723-1733
+//   k_trace    myScene.java:888-903 findClosestRayHit (+ everything under it, see dev_isect.cuh)
+//   k_shade    myScene.java:907-914 reflectRay, :1104-1149 skydome ; myObjShader.java:409-438 / :635-651 getColorAtPos (ambient, texture,
+//              photon term, secondary rays :157-294, :503-631)
+//   k_light    myObjShader.java:98-153 calcShadowColor ; myLight.java:33-41,77-82,159-163,251-266 ; myScene.java:879-885 calcShadow
+//   k_resolve  the return path of the recursion: per-bounce clamp (myObjShader.java:661) then weighting
+//   k_finish   mean of clamped samples, clamp, (int)(c*255) pack (myScene.java:1460, myObjShader.java:671)
+#include "renderer.h"
+#include "dev_shade.cuh"
+#include <cstdio>
+#include <stdexcept>
+#include <vector>
+
+namespace drt {
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x); } while (0)
+
+struct alignas(16) RayRec { double o[3], d[3]; double kt0, kt1; uint32_t ka, kb, kc, stream; int32_t gen, valid; int32_t pad[2]; };
+struct alignas(16) SurfRec { double loc[3], n[3], rawDir[3], tex[3]; int32_t shader, valid; uint32_t ka, kb, kc, stream; int32_t gen, pad; };
+struct alignas(16) NodeRec { double local[3], cA[3], cB[3], w[3]; int32_t parent, slot; int32_t pad[2]; };
+
+struct Counters { unsigned long long primary, shadow, reflect, refract, box, prim, nextCount, pad; };
+
+__device__ __forceinline__ void warpAdd(unsigned long long* dst, unsigned long long v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DScene S, long long pix0, long long nRays, RayRec* __restrict__ rays, NodeRec* __restrict__ nodes) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= nRays) return;
+  const FGlobals& g = S.g; int spp = g.spp < 1 ? 1 : g.spp;
+  long long pix = pix0 + i / spp; uint32_t smp = (uint32_t)(i % spp);
+  int row = (int)(pix / g.cols), col = (int)(pix % g.cols);
+  RayRec r; r.kt0 = 1; r.kt1 = 1; r.ka = (uint32_t)pix; r.kb = smp; r.kc = 1; r.stream = STREAM_PIXEL; r.gen = 0; r.valid = 1; r.pad[0] = r.pad[1] = 0;
+  D3 o = d3(g.eye[0], g.eye[1], g.eye[2]), d = d3(0, 0, -1);
+  auto U = [&](uint32_t dim) { return philoxU01(g.seed, STREAM_PIXEL, (uint32_t)pix, smp, 1, dim); };
+  if (g.spp < 1) r.valid = 0;     // rays_per_pixel 0: the reference averages nothing (0/0 -> NaN -> 0)
+  if (g.camKind == CAM_FOV) {
+    double rayY = (-1 * (row - g.rayYOffset)), rayX = col - g.rayXOffset;
+    if (g.hasDof) {
+      D3 lensCtr = norm3(d3(rayX, rayY, g.viewZ));
+      // focal point: un-jittered pixel ray against plane z = -focalD  (N = (0,0,1), D = focalD)
+      double planeRes = lensCtr.z, tf = -(((0 * o.x) + (0 * o.y)) + (1 * o.z) + g.focalD) / planeRes;
+      D3 focal = d3((lensCtr.x * tf) + o.x, (lensCtr.y * tf) + o.y, (lensCtr.z * tf) + o.z);
+      D3 tmp = norm3(rotAboutAxis(d3(0, 1, 0), d3(0, 0, -1), urange(U(DIM_LENS_ANGLE), 0, DRT_TWO_PI_F)));
+      tmp = scale3(tmp, urange(U(DIM_LENS_RADIUS), 0, g.lensRadius)); o = add3(tmp, lensCtr);
+      d = d3(focal.x - o.x, focal.y - o.y, focal.z - o.z);
+    } else if (spp == 1) d = d3(rayX, rayY, g.viewZ);
+    else { double ry = rayY + urange(U(DIM_AA_Y), -.5, .5), rx = rayX + urange(U(DIM_AA_X), -.5, .5); d = d3(rx, ry, g.viewZ); }
+  } else if (g.camKind == CAM_FISHEYE) {
+    double yVal, xVal;
+    if (spp == 1) { yVal = (row + g.yStart) * g.fishMult; xVal = (col + g.xStart) * g.fishMult; }
+    else { yVal = ((row + g.yStart) + urange(U(DIM_AA_Y), -.5, .5)) * g.fishMult; xVal = ((col + g.xStart) + urange(U(DIM_AA_X), -.5, .5)) * g.fishMult; }
+    double rSq = (spp == 1) ? (xVal * xVal + yVal * yVal) : (yVal * yVal + xVal * xVal);
+    if (rSq > 1) r.valid = 0;
+    else { double rr = sqrt(rSq), theta = rr * g.aperatureHlf, phi = atan2(-yVal, xVal), sTh = sin(theta); d = d3(sTh * cos(phi), sTh * sin(phi), -cos(theta)); }
+  } else {
+    double ryo = g.rows / 2.0, rxo = g.cols / 2.0;
+    if (spp == 1) o = d3(g.orthPerCol * (col - rxo), g.orthPerRow * (-1 * (row - ryo)), 0);
+    else { double yB = g.orthPerRow * ((-1 * (row - ryo)) - .5), xB = g.orthPerCol * (col - rxo - .5);
+      double ry = yB + (g.orthPerRow * urange(U(DIM_AA_Y), -.5, .5)), rx = xB + (g.orthPerCol * urange(U(DIM_AA_X), -.5, .5)); o = d3(rx, ry, 0); }
+    d = d3(0, 0, -1);
+  }
+  d = norm3(d);
+  r.o[0] = o.x; r.o[1] = o.y; r.o[2] = o.z; r.d[0] = d.x; r.d[1] = d.y; r.d[2] = d.z;
+  rays[i] = r;
+  NodeRec n; n.parent = -1; n.slot = 0; n.pad[0] = n.pad[1] = 0;
+  for (int k = 0; k < 3; ++k) { n.local[k] = 0; n.cA[k] = 0; n.cB[k] = 0; n.w[k] = 1; }
+  nodes[i] = n;
+}
+
+__device__ __forceinline__ double rayTime(const DScene& S, uint32_t stream, uint32_t a, uint32_t b, uint32_t c, uint32_t dim) {
+  return S.g.pad0 ? philoxU01(S.g.seed, stream, a, b, c, dim) : 0.0;      // pad0 = scene has moving spheres
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace(const __grid_constant__ DScene S, long long n, const RayRec* __restrict__ rays, Hit* __restrict__ hits, Counters* ctr) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  TraceCounters tc; tc.box = 0; tc.prim = 0;
+  if (i < n) {
+    const RayRec r = rays[i]; Hit h; hitReset(h);
+    if (r.valid) {
+      Ray ray = makeRay(d3(r.o[0], r.o[1], r.o[2]), d3(r.d[0], r.d[1], r.d[2]));
+      closestHit(S, ray, rayTime(S, r.stream, r.ka, r.kb, r.kc, r.stream == STREAM_PIXEL ? DIM_TIME : 0xFFFFu), h, COUNT ? &tc : nullptr);
+    }
+    hits[i] = h;
+  }
+  if (COUNT) { warpAdd(&ctr->box, tc.box); warpAdd(&ctr->prim, tc.prim); }
+}
+
+// skydome lookup for rays that leave the scene (myScene.java:1104-1149): nearest texel, no filtering
+__device__ inline D3 skyColor(const DScene& S, D3 o, D3 d) {
+  const FGlobals& g = S.g; double rx = g.skyRad[0], ry = g.skyRad[1], rz = g.skyRad[2];
+  double dxr = d.x / rx, dyr = d.y / ry, dzr = d.z / rz;
+  double a = ((dxr) * (dxr)) + ((dyr) * (dyr)) + ((dzr) * (dzr));
+  D3 pC = d3((o.x - g.skyOrigin[0]) / rx, (o.y - g.skyOrigin[1]) / ry, (o.z - g.skyOrigin[2]) / rz);
+  double b = 2 * (((dxr) * pC.x) + ((dyr) * pC.y) + ((dzr) * pC.z)), c = (pC.x * pC.x) + (pC.y * pC.y) + (pC.z * pC.z) - 1;
+  double discr = ((b * b) - (4 * a * c)), t = -DRT_DMAX;
+  if (discr > 0) { double d1 = sqrt(discr), t1 = (-1 * b + d1) / (2 * a), t2 = (-1 * b - d1) / (2 * a), tv = jminD(t1, t2); if (tv < DRT_EPS) tv = jmaxD(t1, t2); t = tv; }
+  D3 p = d3((d.x * t) + o.x, (d.y * t) + o.y, (d.z * t) + o.z);
+  const FImage im = S.images[g.skyImage];
+  double a0 = p.y - g.skyOrigin[1], a1 = a0 / ry; a1 = (a1 > 1) ? 1 : (a1 < -1) ? -1 : a1;
+  double v = (im.h - 1) * acos(a1) / DRT_PI;
+  double shWm1 = im.w - 1, z1 = (p.z - g.skyOrigin[2]), q = v / (im.h - 1);
+  double b0 = (p.x - g.skyOrigin[0]) / rx; b0 = (b0 > 1) ? 1 : (b0 < -1) ? -1 : b0;
+  double b1 = sin(q * DRT_PI), b2 = (fabs(b1) < DRT_EPS) ? 1 : b0 / b1;
+  double u = (z1 <= DRT_EPS) ? ((shWm1 * (acos(b2)) / (DRT_TWO_PI_F)) + shWm1 / 2.0f) : shWm1 - ((shWm1 * (acos(b2)) / (DRT_TWO_PI_F)) + shWm1 / 2.0f);
+  u = (u < 0) ? 0 : (u > shWm1) ? shWm1 : u;
+  long long idx = (long long)j2iD(v) * im.w + j2iD(u), n = (long long)im.w * im.h; idx = idx < 0 ? 0 : (idx >= n ? n - 1 : idx);
+  return colorOfArgb(S.texels[im.offset + idx]);
+}
+
+// photon radiance estimate, defined in photon.cuh (hash-grid kNN gather)
+__device__ D3 photonIrradiance(const DScene& S, D3 p);
+
+// Surface pass. One thread per ray of the level; children go to the next level's queue.
+__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene S, long long n, const RayRec* __restrict__ rays, const Hit* __restrict__ hits,
+                                               SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, RayRec* __restrict__ nextRays, NodeRec* __restrict__ nextNodes,
+                                               Counters* ctr, long long nextCap) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int nChild = 0; RayRec ch[2]; NodeRec cn[2];
+  unsigned long long cPrimary = 0, cRefl = 0, cRefr = 0;
+  if (i < n) {
+    const RayRec r = rays[i]; const Hit h = hits[i];
+    SurfRec s; s.valid = 0; s.shader = -1; s.ka = r.ka; s.kb = r.kb; s.kc = r.kc; s.stream = r.stream; s.gen = r.gen; s.pad = 0;
+    D3 local = d3(0, 0, 0);
+    if (r.valid) {
+      if (r.gen == 0) cPrimary = 1;
+      if (h.prim < 0) {
+        if (S.g.hasSky) local = skyColor(S, d3(r.o[0], r.o[1], r.o[2]), d3(r.d[0], r.d[1], r.d[2]));
+        else local = d3(S.g.bg[0], S.g.bg[1], S.g.bg[2]);
+      } else {
+        const FPrim P = S.prims[h.prim]; const FXform& X = S.xforms[h.hitXform];
+        const int shIdx = h.shaderOverride >= 0 ? h.shaderOverride : P.shader; const FShader sh = S.shaders[shIdx];
+        D3 fwd = xfPoint(X.m, h.loc);
+        D3 nrm = norm3(xfVector(X.adj, primNormal(S, P, h.loc, h.arg0, h.arg1, h.state)));
+        local = d3(sh.amb[0], sh.amb[1], sh.amb[2]);
+        const bool simple = (sh.flags & SF_SIMPLE) != 0;
+        if (!simple && (sh.KRefl == 0.0) && (sh.flags & SF_USE_PHOTON) && S.numPhotons > 0) {
+          D3 irr = photonIrradiance(S, fwd);
+          if (sh.flags & SF_IS_CAUSTIC_PHTN) local = add3(local, irr);
+          else local = d3(local.x + sh.diff[0] * irr.x, local.y + sh.diff[1] * irr.y, local.z + sh.diff[2] * irr.z);
+        }
+        double time = rayTime(S, r.stream, r.ka, r.kb, r.kc, DIM_TIME);
+        D3 tex = evalTexture(S, sh, P, h.loc, fwd, h.state, time);
+        s.valid = 1; s.shader = shIdx;
+        s.loc[0] = fwd.x; s.loc[1] = fwd.y; s.loc[2] = fwd.z; s.n[0] = nrm.x; s.n[1] = nrm.y; s.n[2] = nrm.z;
+        s.rawDir[0] = h.rawDir.x; s.rawDir[1] = h.rawDir.y; s.rawDir[2] = h.rawDir.z; s.tex[0] = tex.x; s.tex[1] = tex.y; s.tex[2] = tex.z;
+        // secondary rays (leave room for the shadow generation: gen < numRays - 2)
+        if ((r.gen < S.g.numRays - 2) && (sh.flags & SF_HAS_CAUSTIC)) {
+          auto child = [&](int slot, D3 dir, D3 w, double kt0, double kt1) {
+            RayRec& c = ch[nChild]; NodeRec& nn = cn[nChild]; ++nChild;
+            D3 dn = norm3(dir);
+            c.o[0] = fwd.x; c.o[1] = fwd.y; c.o[2] = fwd.z; c.d[0] = dn.x; c.d[1] = dn.y; c.d[2] = dn.z; c.kt0 = kt0; c.kt1 = kt1;
+            c.ka = r.ka; c.kb = r.kb; c.kc = r.kc * 2 + (slot == 1 ? 1 : 0); c.stream = r.stream; c.gen = r.gen + 1; c.valid = 1; c.pad[0] = c.pad[1] = 0;
+            nn.parent = (int32_t)i; nn.slot = slot; nn.pad[0] = nn.pad[1] = 0; nn.w[0] = w.x; nn.w[1] = w.y; nn.w[2] = w.z;
+            for (int k = 0; k < 3; ++k) { nn.local[k] = 0; nn.cA[k] = 0; nn.cB[k] = 0; }
+          };
+          D3 perm = d3(sh.perm[0], sh.perm[1], sh.perm[2]);
+          bool trans = simple ? (sh.KTrans > 0) : ((sh.KTrans > 0) || (sh.currPerm > 0.0));
+          if (trans) {
+            Fres f = simple ? fresnel(h.rawDir, nrm, sh.currPerm, r.kt1) : fresnel(h.rawDir, nrm, sh.KTrans, r.kt0);
+            const double thr = simple ? 0.0 : DRT_EPS;
+            if (f.oneM > thr) { D3 w = simple ? d3(f.oneM * sh.KTrans, f.oneM * sh.KTrans, f.oneM * sh.KTrans) : d3((f.oneM) * perm.x, (f.oneM) * perm.y, (f.oneM) * perm.z);
+              child(1, refractDir(f), w, sh.KTrans, sh.currPerm); cRefr = 1; }
+            if (f.ratio > thr) { D3 rd = scale3(reflDir(f.back, f.N), f.mult);
+              D3 w = simple ? d3(f.ratio * sh.KRefl, f.ratio * sh.KRefl, f.ratio * sh.KRefl) : d3((f.ratio) * perm.x, (f.ratio) * perm.y, (f.ratio) * perm.z);
+              if (simple) child(2, rd, w, 1, 1); else child(2, rd, w, sh.KTrans, sh.currPerm); cRefl = 1; }
+          } else if (sh.KRefl > 0.0) {
+            D3 back = scale3(h.rawDir, -1); D3 rd = reflDir(back, nrm);
+            if (dot3(rd, nrm) >= 0) { child(2, rd, d3(sh.kreflClr[0], sh.kreflClr[1], sh.kreflClr[2]), 1, 1); cRefl = 1; }
+          }
+        }
+      }
+    }
+    surf[i] = s;
+    nodes[i].local[0] = local.x; nodes[i].local[1] = local.y; nodes[i].local[2] = local.z;
+  }
+  // warp-aggregated compaction of the children into the next level's queue
+  unsigned lane = threadIdx.x & 31;
+  int incl = nChild;
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += v; }
+  int total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned long long base = 0;
+  if (total > 0) { if (lane == 31) base = atomicAdd(&ctr->nextCount, (unsigned long long)total); base = __shfl_sync(0xffffffffu, base, 31); }
+  long long at = (long long)base + (incl - nChild);
+  for (int k = 0; k < nChild; ++k) if (at + k < nextCap) { nextRays[at + k] = ch[k]; nextNodes[at + k] = cn[k]; }
+  warpAdd(&ctr->primary, cPrimary); warpAdd(&ctr->reflect, cRefl); warpAdd(&ctr->refract, cRefr);
+}
+
+// Light pass: literal calcShadowColor, one thread per shaded hit, lights in list order, shadow rays traced in-thread.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_light(const __grid_constant__ DScene S, long long n, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, Counters* ctr) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  TraceCounters tc; tc.box = 0; tc.prim = 0; unsigned long long cShadow = 0;
+  if (i < n) {
+    const SurfRec s = surf[i];
+    if (s.valid) {
+      const FShader sh = S.shaders[s.shader];
+      D3 hitLoc = d3(s.loc[0], s.loc[1], s.loc[2]), N = d3(s.n[0], s.n[1], s.n[2]), rawDir = d3(s.rawDir[0], s.rawDir[1], s.rawDir[2]);
+      double r = 0, g = 0, b = 0;
+      for (int li = 0; li < S.g.numLights; ++li) {
+        const FLight L = S.lights[li]; const FXform& LX = S.xforms[L.xform];
+        const uint32_t dim = DIM_LIGHT_BASE + DIM_LIGHT_STRIDE * li;
+        D3 lo = d3(L.origin[0], L.origin[1], L.origin[2]), orient = d3(L.orient[0], L.orient[1], L.orient[2]);
+        auto diskPos = [&](uint32_t d0) {           // myDiskLight.getRandomDiskPos (:251-258)
+          double ua = philoxU01(S.g.seed, s.stream, s.ka, s.kb, s.kc, d0), ur = philoxU01(S.g.seed, s.stream, s.ka, s.kb, s.kc, d0 + 1);
+          D3 tmp = norm3(rotAboutAxis(d3(L.tangent[0], L.tangent[1], L.tangent[2]), orient, urange(ua, 0, DRT_TWO_PI_F)));
+          return add3(scale3(tmp, urange(ur, 0, L.radius)), lo);
+        };
+        D3 target = (L.type == LT_DISK) ? diskPos(dim) : lo;
+        D3 lightNorm = norm3(sub3(xfPoint(LX.m, target), hitLoc));
+        Ray shadowRay = makeRay(hitLoc, lightNorm);
+        // light.intersectCheck: distance to the light's (re-sampled, untransformed) origin, penumbra factor
+        D3 dOrg = (L.type == LT_DISK) ? diskPos(dim + 2) : lo;
+        double t = sqrt(((hitLoc.x - dOrg.x) * (hitLoc.x - dOrg.x)) + ((hitLoc.y - dOrg.y) * (hitLoc.y - dOrg.y)) + ((hitLoc.z - dOrg.z) * (hitLoc.z - dOrg.z)));
+        double ltMult = 1;
+        if (L.type == LT_SPOT) { double angle = acos(-1 * dot3(lightNorm, orient)); ltMult = (angle < L.innerRad) ? 1 : (angle > L.outerRad) ? 0 : (L.outerRad - angle) / L.radDiff; }
+        if (ltMult == 0) continue;
+        ++cShadow;
+        double time = rayTime(S, s.stream, s.ka, s.kb, s.kc, dim + 4);
+        if (!anyHit(S, shadowRay, time, t, COUNT ? &tc : nullptr)) {
+          double ld = dot3(lightNorm, N) * ltMult;
+          if (ld > DRT_EPS) { r += s.tex[0] * L.color[0] * ld; g += s.tex[1] * L.color[1] * ld; b += s.tex[2] * L.color[2] * ld; }
+          if (sh.phong == 0) continue;
+          D3 hN = norm3(sub3(lightNorm, rawDir));
+          double hd = dot3(hN, N) * ltMult;
+          if (hd > DRT_EPS) { double ph = pow(hd * hd, sh.phong); r += sh.spec[0] * L.color[0] * ph; g += sh.spec[1] * L.color[1] * ph; b += sh.spec[2] * L.color[2] * ph; }
+        }
+      }
+      nodes[i].local[0] += r; nodes[i].local[1] += g; nodes[i].local[2] += b;
+    }
+  }
+  warpAdd(&ctr->shadow, cShadow);
+  if (COUNT) { warpAdd(&ctr->box, tc.box); warpAdd(&ctr->prim, tc.prim); }
+}
+
+__device__ __forceinline__ D3 nodeTotal(const NodeRec& nd) {
+  return clampColor1(d3(nd.local[0] + (nd.cA[0] + nd.cB[0]), nd.local[1] + (nd.cA[1] + nd.cB[1]), nd.local[2] + (nd.cA[2] + nd.cB[2])));
+}
+// level L -> level L-1: parent.slot = w (.) clamp1(total(child))
+__global__ void k_resolve(long long n, const NodeRec* __restrict__ lvl, NodeRec* __restrict__ parentLvl) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  const NodeRec nd = lvl[i]; D3 c = nodeTotal(nd);
+  double* dst = (nd.slot == 1) ? parentLvl[nd.parent].cA : parentLvl[nd.parent].cB;
+  dst[0] = nd.w[0] * c.x; dst[1] = nd.w[1] * c.y; dst[2] = nd.w[2] * c.z;
+}
+__global__ void k_finish(const __grid_constant__ DScene S, long long pix0, long long nPix, const NodeRec* __restrict__ roots, const Hit* __restrict__ hits0, RenderOutputs out) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (p >= nPix) return;
+  int spp = S.g.spp < 1 ? 1 : S.g.spp; double r = 0, g = 0, b = 0;
+  for (int s = 0; s < spp; ++s) { D3 c = nodeTotal(roots[p * spp + s]); r += c.x; g += c.y; b += c.z; }
+  D3 c;
+  if (S.g.spp < 1) c = d3(0, 0, 0);
+  else c = clampColor1(d3(r / spp, g / spp, b / spp));
+  long long q = pix0 + p;
+  if (out.argb) out.argb[q] = packArgb(c);
+  if (out.rgb) { out.rgb[3 * q] = c.x; out.rgb[3 * q + 1] = c.y; out.rgb[3 * q + 2] = c.z; }
+  if (out.hitPrim || out.hitInst || out.t) {
+    const Hit h = hits0[p * spp];
+    if (out.hitPrim) out.hitPrim[q] = h.prim >= 0 ? S.prims[h.prim].serial : -1;
+    if (out.hitInst) out.hitInst[q] = h.prim >= 0 ? h.inst : -1;
+    if (out.t) out.t[q] = h.prim >= 0 ? h.t : 0;
+  }
+}
+
+// parity helpers ------------------------------------------------------------------------------------------------
+__global__ void k_trace_explicit(const __grid_constant__ DScene S, long long n, const double* __restrict__ org, const double* __restrict__ dir, int32_t* __restrict__ ids, double* __restrict__ tOut) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  Ray ray = makeRay(d3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), norm3(d3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2])));
+  Hit h; closestHit(S, ray, 0.0, h, nullptr);
+  ids[2 * i] = h.prim >= 0 ? S.prims[h.prim].serial : -1; ids[2 * i + 1] = h.prim >= 0 ? h.inst : -1; tOut[i] = h.prim >= 0 ? h.t : 0;
+}
+__global__ void k_eval_texture(const __grid_constant__ DScene S, int shader, long long n, const double* __restrict__ hl, const double* __restrict__ fl, double* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  FPrim P; P.type = PT_BOX; P.flags = 0; P.xform = 0; P.shader = shader; P.data = 0; P.serial = 0; P.pad0 = P.pad1 = 0;   // no image textures through this probe
+  D3 c = evalTexture(S, S.shaders[shader], P, d3(hl[3 * i], hl[3 * i + 1], hl[3 * i + 2]), d3(fl[3 * i], fl[3 * i + 1], fl[3 * i + 2]), 0, 0.0);
+  out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+}
+
+}  // namespace drt
+
+#include "photon.cuh"
+
+namespace drt {
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+template <class T> struct DBuf {
+  T* p = nullptr; size_t cap = 0;
+  void ensure(size_t n, cudaStream_t st, bool keep = false) {
+    if (n <= cap) return;
+    size_t nc = n + n / 4 + 1024; T* q = nullptr; CK(cudaMalloc(&q, nc * sizeof(T)));
+    if (keep && p && cap) CK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    if (p) { CK(cudaStreamSynchronize(st)); CK(cudaFree(p)); }
+    p = q; cap = nc;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <class T> static const T* uploadVec(const std::vector<T>& v, std::vector<void*>& owned, cudaStream_t st) {
+  T* d = nullptr; size_t n = v.size() ? v.size() : 1;
+  CK(cudaMalloc(&d, n * sizeof(T))); owned.push_back(d);
+  if (v.size()) CK(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  return d;
+}
+
+struct Renderer::Impl {
+  DScene ds; std::vector<void*> owned;
+  DBuf<RayRec> rays[2]; DBuf<Hit> hits; DBuf<Hit> hits0; DBuf<SurfRec> surf; DBuf<NodeRec> nodes; Counters* ctr = nullptr; Counters* ctrHost = nullptr;
+  DBuf<int32_t> oArgb, oPrim, oInst; DBuf<double> oRgb, oT;
+  cudaEvent_t ev[8];
+  PhotonMap photons;
+  size_t sceneBytes = 0;
+};
+
+Renderer::Renderer(int device) : impl_(new Impl), device_(device) {
+  int cnt = 0; cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0) { delete impl_; throw std::runtime_error("no CUDA device available: this renderer has no CPU fallback"); }
+  CK(cudaSetDevice(device));
+  cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); stream_ = st;
+  CK(cudaMalloc(&impl_->ctr, sizeof(Counters))); CK(cudaMallocHost(&impl_->ctrHost, sizeof(Counters)));
+  for (auto& e2 : impl_->ev) CK(cudaEventCreate(&e2));
+  std::memset(&impl_->ds, 0, sizeof(DScene)); std::memset(&g_, 0, sizeof(g_));
+  static const unsigned char p[256] = {151,160,137,91,90,15,131,13,201,95,96,53,194,233,7,225,140,36,103,30,69,142,8,99,37,240,21,10,23,190,6,148,247,120,234,75,0,26,197,62,94,252,219,203,117,35,11,32,57,177,33,88,237,149,56,87,174,20,125,136,171,168,68,175,74,165,71,134,139,48,27,166,77,146,158,231,83,111,229,122,60,211,133,230,220,105,92,41,55,46,245,40,244,102,143,54,65,25,63,161,1,216,80,73,209,76,132,187,208,89,18,169,200,196,135,130,116,188,159,86,164,100,109,198,173,186,3,64,52,217,226,250,124,123,5,202,38,147,118,126,255,82,85,212,207,206,59,227,47,16,58,17,182,189,28,42,223,183,170,213,119,248,152,2,44,154,163,70,221,153,101,155,167,43,172,9,129,22,39,253,19,98,108,110,79,113,224,232,178,185,112,104,218,246,97,228,251,34,242,193,238,210,144,12,191,179,162,241,81,51,145,235,249,14,239,107,49,192,214,31,181,199,106,157,184,84,204,176,115,121,50,45,127,4,150,254,138,236,205,93,222,114,67,29,24,72,243,141,128,195,78,66,215,61,156,180};
+  unsigned char perm[512]; for (int i = 0; i < 512; ++i) perm[i] = p[i & 255];
+  CK(cudaMemcpyToSymbol(c_perm, perm, 512));
+}
+Renderer::~Renderer() {
+  cudaSetDevice(device_);
+  for (void* p : impl_->owned) cudaFree(p);
+  impl_->rays[0].release(); impl_->rays[1].release(); impl_->hits.release(); impl_->hits0.release(); impl_->surf.release(); impl_->nodes.release();
+  impl_->oArgb.release(); impl_->oPrim.release(); impl_->oInst.release(); impl_->oRgb.release(); impl_->oT.release();
+  impl_->photons.release();
+  cudaFree(impl_->ctr); cudaFreeHost(impl_->ctrHost);
+  for (auto& e : impl_->ev) cudaEventDestroy(e);
+  cudaStreamDestroy((cudaStream_t)stream_); delete impl_;
+}
+
+void Renderer::upload(const HostScene& hs) {
+  CK(cudaSetDevice(device_)); cudaStream_t st = (cudaStream_t)stream_;
+  CK(cudaStreamSynchronize(st));
+  for (void* p : impl_->owned) cudaFree(p); impl_->owned.clear();
+  // device-side nesting limits (see dev_isect.cuh): accel children are primitives or instances; an instanced accel holds primitives
+  for (const FInstance& in : hs.instances) if (in.baseKind == OK_LIST || in.baseKind == OK_BVH) {
+    auto checkList = [&](const FList& L) { for (int i = 0; i < L.childCount; ++i) { const FObjRef& c = hs.children[L.childStart + i];
+      if (c.kind == OK_INSTANCE && hs.instances[c.idx].baseKind != OK_PRIM) throw std::runtime_error("instances nested deeper than TLAS->instance->BLAS are not supported on the device"); } };
+    if (in.baseKind == OK_LIST) checkList(hs.lists[in.baseIdx]);
+    else { std::vector<int32_t> st2{hs.bvhs[in.baseIdx].root}; while (!st2.empty()) { int32_t r = st2.back(); st2.pop_back(); if (r < 0) checkList(hs.lists[~r]); else { st2.push_back(hs.nodes[r].left); st2.push_back(hs.nodes[r].right); } } }
+  }
+  DScene& d = impl_->ds; auto& ow = impl_->owned;
+  d.xforms = uploadVec(hs.xforms, ow, st); d.prims = uploadVec(hs.prims, ow, st); d.pdata = uploadVec(hs.pdata, ow, st); d.top = uploadVec(hs.top, ow, st);
+  d.children = uploadVec(hs.children, ow, st); d.instances = uploadVec(hs.instances, ow, st); d.lists = uploadVec(hs.lists, ow, st); d.bvhs = uploadVec(hs.bvhs, ow, st);
+  d.nodes = uploadVec(hs.nodes, ow, st); d.lights = uploadVec(hs.lights, ow, st); d.shaders = uploadVec(hs.shaders, ow, st); d.textures = uploadVec(hs.textures, ow, st);
+  d.texColors = uploadVec(hs.texColors, ow, st); d.images = uploadVec(hs.images, ow, st); d.texels = uploadVec(hs.texels, ow, st);
+  impl_->sceneBytes = hs.xforms.size() * sizeof(FXform) + hs.prims.size() * sizeof(FPrim) + hs.pdata.size() * 8 + hs.children.size() * sizeof(FObjRef) + hs.nodes.size() * sizeof(FNode) + hs.lists.size() * sizeof(FList) + hs.texels.size() * 4;
+  d.g = hs.g; d.g.pad0 = 0;
+  for (const FPrim& p : hs.prims) if (p.type == PT_MOVSPHERE) d.g.pad0 = 1;
+  d.numPhotons = 0; d.phPos = nullptr; d.phPwr = nullptr; d.cellStart = nullptr; d.cellEnd = nullptr;
+  g_ = d.g;
+  impl_->photons.reset();
+  CK(cudaStreamSynchronize(st));
+}
+
+static inline unsigned gridFor(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+void Renderer::renderRange(long long pix0, long long pix1, const RenderOutputs& out, RenderStats* stats) {
+  CK(cudaSetDevice(device_)); cudaStream_t st = (cudaStream_t)stream_; Impl& I = *impl_;
+  if (!I.ds.prims) throw std::runtime_error("render called before a scene was uploaded");
+  if (g_.photonKind != 0 && !I.photons.built) { I.photons.emitAndBuild(I.ds, st, stats); }
+  const int spp = g_.spp < 1 ? 1 : g_.spp;
+  long long pixPerBatch = batchRays_ / spp; if (pixPerBatch < 1) pixPerBatch = 1;
+  RenderStats rs; std::memset(&rs, 0, sizeof(rs)); if (stats) { rs.photonSeg = stats->photonSeg; rs.photonsStored = stats->photonsStored; }
+  rs.photonsStored = I.photons.count;
+  float msT = 0, msS = 0, msL = 0;
+  CK(cudaEventRecord(I.ev[0], st));
+  for (long long b0 = pix0; b0 < pix1; b0 += pixPerBatch) {
+    long long nPix = std::min(pixPerBatch, pix1 - b0), n0 = nPix * spp;
+    CK(cudaMemsetAsync(I.ctr, 0, sizeof(Counters), st));
+    std::vector<long long> lvlCount, lvlOff; long long n = n0, off = 0; int cur = 0;
+    I.rays[0].ensure(n0, st); I.nodes.ensure(n0, st, false); I.hits0.ensure(n0, st);
+    k_raygen<<<gridFor(n0, 256), 256, 0, st>>>(I.ds, b0, n0, I.rays[0].p, I.nodes.p); ++rs.kernelLaunches;
+    for (int level = 0; n > 0; ++level) {
+      lvlCount.push_back(n); lvlOff.push_back(off);
+      Hit* hitBuf; if (level == 0) hitBuf = I.hits0.p; else { I.hits.ensure(n, st); hitBuf = I.hits.p; }
+      I.surf.ensure(n, st);
+      long long nextCap = 2 * n; I.rays[cur ^ 1].ensure(nextCap, st); I.nodes.ensure(off + n + nextCap, st, true);
+      CK(cudaEventRecord(I.ev[1], st));
+      if (counters_) k_trace<true><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.rays[cur].p, hitBuf, I.ctr);
+      else k_trace<false><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.rays[cur].p, hitBuf, I.ctr);
+      CK(cudaEventRecord(I.ev[2], st));
+      k_shade<<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.rays[cur].p, hitBuf, I.surf.p, I.nodes.p + off, I.rays[cur ^ 1].p, I.nodes.p + off + n, I.ctr, nextCap);
+      CK(cudaEventRecord(I.ev[3], st));
+      if (counters_) k_light<true><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off, I.ctr);
+      else k_light<false><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off, I.ctr);
+      CK(cudaEventRecord(I.ev[4], st));
+      rs.kernelLaunches += 3;
+      CK(cudaMemcpyAsync(I.ctrHost, I.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      float a, b2, c; CK(cudaEventElapsedTime(&a, I.ev[1], I.ev[2])); CK(cudaEventElapsedTime(&b2, I.ev[2], I.ev[3])); CK(cudaEventElapsedTime(&c, I.ev[3], I.ev[4]));
+      msT += a; msS += b2; msL += c;
+      long long next = (long long)I.ctrHost->nextCount; if (next > nextCap) next = nextCap;
+      CK(cudaMemsetAsync(&I.ctr->nextCount, 0, sizeof(unsigned long long), st));
+      off += n; n = next; cur ^= 1;
+    }
+    for (int level = (int)lvlCount.size() - 1; level >= 1; --level) {
+      k_resolve<<<gridFor(lvlCount[level], 256), 256, 0, st>>>(lvlCount[level], I.nodes.p + lvlOff[level], I.nodes.p + lvlOff[level - 1]); ++rs.kernelLaunches;
+    }
+    k_finish<<<gridFor(nPix, 256), 256, 0, st>>>(I.ds, b0, nPix, I.nodes.p, I.hits0.p, out); ++rs.kernelLaunches;
+    CK(cudaMemcpyAsync(I.ctrHost, I.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    rs.primary += I.ctrHost->primary; rs.shadow += I.ctrHost->shadow; rs.reflect += I.ctrHost->reflect; rs.refract += I.ctrHost->refract; rs.boxTests += I.ctrHost->box; rs.primTests += I.ctrHost->prim;
+  }
+  CK(cudaEventRecord(I.ev[5], st)); CK(cudaStreamSynchronize(st));
+  float tot; CK(cudaEventElapsedTime(&tot, I.ev[0], I.ev[5]));
+  CK(cudaGetLastError());
+  rs.msTrace = msT; rs.msShade = msS; rs.msLight = msL; rs.msTotal = tot; rs.msOther = tot - msT - msS - msL;
+  if (stats) *stats = rs;
+}
+
+void Renderer::renderToHost(int32_t* argbHost, int32_t* hitPrimHost, int32_t* hitInstHost, double* rgbHost, double* tHost, RenderStats* stats) {
+  CK(cudaSetDevice(device_)); cudaStream_t st = (cudaStream_t)stream_; Impl& I = *impl_;
+  size_t np = (size_t)g_.cols * g_.rows; RenderOutputs o; std::memset(&o, 0, sizeof(o));
+  if (argbHost) { I.oArgb.ensure(np, st); o.argb = I.oArgb.p; } if (hitPrimHost) { I.oPrim.ensure(np, st); o.hitPrim = I.oPrim.p; }
+  if (hitInstHost) { I.oInst.ensure(np, st); o.hitInst = I.oInst.p; } if (rgbHost) { I.oRgb.ensure(3 * np, st); o.rgb = I.oRgb.p; } if (tHost) { I.oT.ensure(np, st); o.t = I.oT.p; }
+  renderRange(0, (long long)np, o, stats);
+  if (argbHost) CK(cudaMemcpyAsync(argbHost, o.argb, np * 4, cudaMemcpyDeviceToHost, st));
+  if (hitPrimHost) CK(cudaMemcpyAsync(hitPrimHost, o.hitPrim, np * 4, cudaMemcpyDeviceToHost, st));
+  if (hitInstHost) CK(cudaMemcpyAsync(hitInstHost, o.hitInst, np * 4, cudaMemcpyDeviceToHost, st));
+  if (rgbHost) CK(cudaMemcpyAsync(rgbHost, o.rgb, np * 24, cudaMemcpyDeviceToHost, st));
+  if (tHost) CK(cudaMemcpyAsync(tHost, o.t, np * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+}
+
+double hostPhiloxU01(uint64_t seed, uint32_t stream, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return philoxU01(seed, stream, a, b, c, d); }
+void Renderer::emitPhotons(RenderStats* stats) {
+  CK(cudaSetDevice(device_)); Impl& I = *impl_;
+  if (g_.photonKind != 0 && !I.photons.built) I.photons.emitAndBuild(I.ds, (cudaStream_t)stream_, stats);
+  if (stats) stats->photonsStored = I.photons.count;
+}
+long long Renderer::getPhotons(double* out6Host, long long cap) { CK(cudaSetDevice(device_)); return impl_->photons.download(out6Host, cap, (cudaStream_t)stream_); }
+
+void Renderer::traceRays(long long n, const double* orgHost, const double* dirHost, int32_t* idsHost, double* tHost) {
+  CK(cudaSetDevice(device_)); cudaStream_t st = (cudaStream_t)stream_;
+  double *o, *d, *t; int32_t* ids; CK(cudaMalloc(&o, n * 24)); CK(cudaMalloc(&d, n * 24)); CK(cudaMalloc(&t, n * 8)); CK(cudaMalloc(&ids, n * 8));
+  CK(cudaMemcpyAsync(o, orgHost, n * 24, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(d, dirHost, n * 24, cudaMemcpyHostToDevice, st));
+  k_trace_explicit<<<gridFor(n, 128), 128, 0, st>>>(impl_->ds, n, o, d, ids, t);
+  CK(cudaMemcpyAsync(idsHost, ids, n * 8, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(tHost, t, n * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+  cudaFree(o); cudaFree(d); cudaFree(t); cudaFree(ids);
+}
+void Renderer::evalTexture(int shaderIdx, long long n, const double* hitLocHost, const double* fwdLocHost, double* outHost) {
+  CK(cudaSetDevice(device_)); cudaStream_t st = (cudaStream_t)stream_;
+  double *a, *b, *c; CK(cudaMalloc(&a, n * 24)); CK(cudaMalloc(&b, n * 24)); CK(cudaMalloc(&c, n * 24));
+  CK(cudaMemcpyAsync(a, hitLocHost, n * 24, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(b, fwdLocHost, n * 24, cudaMemcpyHostToDevice, st));
+  k_eval_texture<<<gridFor(n, 128), 128, 0, st>>>(impl_->ds, shaderIdx, n, a, b, c);
+  CK(cudaMemcpyAsync(outHost, c, n * 24, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+  cudaFree(a); cudaFree(b); cudaFree(c);
+}
+
+}  // namespace drt

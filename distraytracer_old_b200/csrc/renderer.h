@@ -1,0 +1,54 @@
+// Host-side handle of the wavefront renderer (device memory owner + kernel launcher).
+#pragma once
+#include "host_scene.h"
+#include <string>
+
+namespace drt {
+
+struct RenderStats {
+  unsigned long long primary, shadow, reflect, refract, photonSeg;   // logical rays
+  unsigned long long boxTests, primTests;                           // only when counters are enabled
+  unsigned long long photonsStored;
+  unsigned long long kernelLaunches;
+  double msTrace, msShade, msLight, msOther, msTotal;               // CUDA-event times of the last render call
+};
+
+struct RenderOutputs {           // device pointers, any may be null; sized cols*rows (rgb: 3x)
+  int32_t* argb; int32_t* hitPrim; int32_t* hitInst; double* rgb; double* t;
+};
+
+class Renderer {
+ public:
+  Renderer(int device);
+  ~Renderer();
+  void upload(const HostScene& hs);                    // flat scene -> HBM
+  void setBatchRays(long long n) { batchRays_ = n; }
+  void setCounters(bool on) { counters_ = on; }
+  void setTraceMode(int m) { traceMode_ = m; }
+  // render pixels [pix0, pix1) (row-major pixel indices) into the device buffers of `out` (indexed by absolute pixel)
+  void renderRange(long long pix0, long long pix1, const RenderOutputs& out, RenderStats* stats);
+  // full frame to host memory (D2H inside)
+  void renderToHost(int32_t* argbHost, int32_t* hitPrimHost, int32_t* hitInstHost, double* rgbHost, double* tHost, RenderStats* stats);
+  // explicit world-space rays (closest hit only) for parity tests: ids = {primSerial, instSerial} per ray
+  void traceRays(long long n, const double* orgHost, const double* dirHost, int32_t* idsHost, double* tHost);
+  void evalTexture(int shaderIdx, long long n, const double* hitLocHost, const double* fwdLocHost, double* outHost);
+  void emitPhotons(RenderStats* stats);               // builds the photon map if the scene asks for one
+  long long getPhotons(double* out6Host, long long cap);
+  int cols() const { return g_.cols; }
+  int rows() const { return g_.rows; }
+  int spp() const { return g_.spp; }
+  void* stream() const { return stream_; }
+  const FGlobals& globals() const { return g_; }
+  struct Impl;
+
+ private:
+  Impl* impl_;
+  FGlobals g_;
+  int device_;
+  void* stream_;
+  long long batchRays_ = 8ll << 20;
+  bool counters_ = false;
+  int traceMode_ = 0;
+};
+
+}  // namespace drt

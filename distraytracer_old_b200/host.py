@@ -1,0 +1,296 @@
+"""ctypes host over include/drt.h.  No torch types cross the boundary; torch is only used by callers that
+want device-resident outputs (multi-GPU tile gather)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SCENES_DIR = os.path.join(ROOT, "scenes")
+TEX_DIR = os.path.join(SCENES_DIR, "txtrs")
+
+ACCEL_REFERENCE, ACCEL_REFERENCE_FAST, ACCEL_LBVH = 0, 1, 2
+
+
+class DrtError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("cols", C.c_int32), ("rows", C.c_int32), ("counters", C.c_int32),
+                ("seed", C.c_uint64), ("batch_rays", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rays_primary", "rays_shadow", "rays_reflect", "rays_refract", "rays_photon",
+                                           "box_tests", "prim_tests", "photons_stored", "kernel_launches")] + \
+               [(n, C.c_double) for n in ("ms_trace", "ms_shade", "ms_light", "ms_other", "ms_total")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+    @property
+    def rays_total(self):
+        return self.rays_primary + self.rays_shadow + self.rays_reflect + self.rays_refract + self.rays_photon
+
+
+_LOADER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_int32)))
+
+_lib = None
+
+
+def lib_path():
+    return os.path.join(HERE, "libdrt.so")
+
+
+def load_library():
+    """Load libdrt.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise DrtError("libdrt.so is not built (run `python -m distraytracer_old_b200.build` or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(p)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    sig = {
+        "drt_create": (C.c_int, [C.POINTER(_Config), C.POINTER(vp)]),
+        "drt_destroy": (None, [vp]),
+        "drt_last_error": (C.c_char_p, [vp]),
+        "drt_set_image_loader": (C.c_int, [vp, _LOADER, vp]),
+        "drt_set_texture_dir": (C.c_int, [vp, C.c_char_p]),
+        "drt_scene_reset": (C.c_int, [vp]),
+        "drt_scene_command": (C.c_int, [vp, C.c_char_p]),
+        "drt_scene_load_cli": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
+        "drt_scene_override": (C.c_int, [vp, i32, i64]),
+        "drt_scene_finalize": (C.c_int, [vp, i32]),
+        "drt_scene_reupload": (C.c_int, [vp]),
+        "drt_scene_info": (C.c_int, [vp, C.POINTER(i32)]),
+        "drt_emit_photons": (C.c_int, [vp, C.POINTER(Stats)]),
+        "drt_render": (C.c_int, [vp, vp, C.POINTER(Stats)]),
+        "drt_render_aov": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(Stats)]),
+        "drt_render_device": (C.c_int, [vp, i64, i64, vp, C.POINTER(Stats)]),
+        "drt_save_png": (C.c_int, [C.c_char_p, vp, i32, i32]),
+        "drt_trace_rays": (C.c_int, [vp, i64, vp, vp, vp, vp]),
+        "drt_eval_texture": (C.c_int, [vp, i32, i64, vp, vp, vp]),
+        "drt_dump_bvh": (i64, [vp, i32, vp, i64, vp]),
+        "drt_obj_ctm": (C.c_int, [vp, i32, vp]),
+        "drt_sample_u01": (dbl, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+        "drt_get_photons": (i64, [vp, vp, i64]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTS = ["drt_create", "drt_destroy", "drt_last_error", "drt_set_image_loader", "drt_set_texture_dir", "drt_scene_reset",
+           "drt_scene_command", "drt_scene_load_cli", "drt_scene_override", "drt_scene_finalize", "drt_scene_reupload",
+           "drt_scene_info", "drt_emit_photons", "drt_render", "drt_render_aov", "drt_render_device", "drt_save_png",
+           "drt_trace_rays", "drt_eval_texture", "drt_dump_bvh", "drt_obj_ctm", "drt_sample_u01", "drt_get_photons"]
+
+
+def decode_image_argb(path):
+    """PApplet.loadImage(...).pixels: ARGB ints with alpha 0xFF."""
+    from PIL import Image
+    im = Image.open(path).convert("RGBA")
+    a = np.asarray(im, dtype=np.uint32)
+    argb = (np.uint32(0xFF) << 24) | (a[..., 0] << 16) | (a[..., 1] << 8) | a[..., 2]
+    return im.width, im.height, np.ascontiguousarray(argb.astype(np.uint32).view(np.int32))
+
+
+class Context:
+    """One renderer context == one GPU (device=-1: host-only, interpreter + flattener, cannot render)."""
+
+    def __init__(self, device=0, cols=300, rows=300, seed=0x5EED, counters=False, batch_rays=0, texture_dir=TEX_DIR):
+        self.L = load_library()
+        cfg = _Config(device, cols, rows, int(counters), seed, batch_rays)
+        h = C.c_void_p()
+        rc = self.L.drt_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise DrtError("drt_create failed (%d): no usable CUDA device and no CPU fallback exists" % rc)
+        self.h = h
+        self.cols, self.rows, self.device = cols, rows, device
+        self._images = {}
+        self._texture_dir = texture_dir
+        self._cb = _LOADER(self._load_image)
+        self._ck(self.L.drt_set_image_loader(self.h, self._cb, None))
+
+    def _load_image(self, user, name, w, h, px):
+        try:
+            key = name.decode()
+            if key not in self._images:
+                self._images[key] = decode_image_argb(os.path.join(self._texture_dir, key))
+            ww, hh, arr = self._images[key]
+            w[0], h[0] = ww, hh
+            px[0] = arr.ctypes.data_as(C.POINTER(C.c_int32))
+            return 0
+        except Exception:
+            return 1
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise DrtError("drt error %d: %s" % (rc, (self.L.drt_last_error(self.h) or b"").decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.drt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Scene:
+    """Mirror of the reference's myScene for the render path."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.L = ctx.L
+        self.finalized = False
+        ctx._ck(self.L.drt_scene_reset(ctx.h))
+
+    @classmethod
+    def from_cli(cls, ctx, file, data_dir=SCENES_DIR, spp=0, photons=-1, accel=ACCEL_REFERENCE, finalize=True):
+        s = cls.__new__(cls)
+        s.ctx, s.L, s.finalized = ctx, ctx.L, False
+        ctx._ck(s.L.drt_scene_load_cli(ctx.h, file.encode(), data_dir.encode()))
+        ctx._ck(s.L.drt_scene_override(ctx.h, spp, photons))
+        if finalize:
+            s.finalize(accel)
+        return s
+
+    def command(self, line):
+        self.ctx._ck(self.L.drt_scene_command(self.ctx.h, line.encode()))
+
+    def override(self, spp=0, photons=-1):
+        self.ctx._ck(self.L.drt_scene_override(self.ctx.h, spp, photons))
+
+    def finalize(self, accel=ACCEL_REFERENCE):
+        self.ctx._ck(self.L.drt_scene_finalize(self.ctx.h, accel))
+        self.finalized = True
+
+    def reupload(self):
+        self.ctx._ck(self.L.drt_scene_reupload(self.ctx.h))
+
+    def info(self):
+        o = (C.c_int32 * 16)()
+        self.ctx._ck(self.L.drt_scene_info(self.ctx.h, o))
+        k = ["cols", "rows", "spp", "top", "lights", "prims", "instances", "photon_kind", "shaders", "nodes", "xforms", "lists", "bvhs", "images", "warnings", "photons_cast"]
+        return dict(zip(k, list(o)))
+
+    # ---- rendering (myScene.draw)
+    def draw(self, aov=False):
+        n = self.ctx.cols * self.ctx.rows
+        st = Stats()
+        argb = np.zeros((self.ctx.rows, self.ctx.cols), dtype=np.int32)
+        if not aov:
+            self.ctx._ck(self.L.drt_render(self.ctx.h, argb.ctypes.data, C.byref(st)))
+            return argb, st
+        hp = np.zeros_like(argb)
+        hi = np.zeros_like(argb)
+        rgb = np.zeros((self.ctx.rows, self.ctx.cols, 3), dtype=np.float64)
+        t = np.zeros((self.ctx.rows, self.ctx.cols), dtype=np.float64)
+        self.ctx._ck(self.L.drt_render_aov(self.ctx.h, argb.ctypes.data, hp.ctypes.data, hi.ctypes.data, rgb.ctypes.data, t.ctypes.data, C.byref(st)))
+        return {"argb": argb, "hit_prim": hp, "hit_inst": hi, "rgb": rgb, "t": t, "stats": st, "pixels": n}
+
+    def draw_into(self, host_argb, stats=None):
+        """Render into a caller-owned (e.g. pinned) int32 host buffer."""
+        st = stats if stats is not None else Stats()
+        self.ctx._ck(self.L.drt_render(self.ctx.h, host_argb, C.byref(st)))
+        return st
+
+    def draw_device(self, pix0, pix1, dev_ptr):
+        st = Stats()
+        self.ctx._ck(self.L.drt_render_device(self.ctx.h, pix0, pix1, dev_ptr, C.byref(st)))
+        return st
+
+    def emit_photons(self):
+        st = Stats()
+        self.ctx._ck(self.L.drt_emit_photons(self.ctx.h, C.byref(st)))
+        return st
+
+    def photons(self, cap=1 << 26):
+        st = self.emit_photons()
+        n = int(st.photons_stored)
+        out = np.zeros((max(n, 1), 6), dtype=np.float64)
+        m = self.L.drt_get_photons(self.ctx.h, out.ctypes.data, min(n, cap))
+        return out[:max(m, 0)]
+
+    def save(self, path, argb):
+        a = np.ascontiguousarray(argb, dtype=np.int32)
+        rc = self.L.drt_save_png(path.encode(), a.ctypes.data, a.shape[1], a.shape[0])
+        if rc != 0:
+            raise DrtError("drt_save_png failed")
+
+    # ---- parity probes
+    def trace_rays(self, org, dirs):
+        org = np.ascontiguousarray(org, dtype=np.float64)
+        dirs = np.ascontiguousarray(dirs, dtype=np.float64)
+        n = org.shape[0]
+        ids = np.zeros((n, 2), dtype=np.int32)
+        t = np.zeros(n, dtype=np.float64)
+        self.ctx._ck(self.L.drt_trace_rays(self.ctx.h, n, org.ctypes.data, dirs.ctypes.data, ids.ctypes.data, t.ctypes.data))
+        return ids, t
+
+    def eval_texture(self, shader_serial, hit_loc, fwd_loc=None):
+        hit_loc = np.ascontiguousarray(hit_loc, dtype=np.float64)
+        fwd_loc = hit_loc if fwd_loc is None else np.ascontiguousarray(fwd_loc, dtype=np.float64)
+        out = np.zeros_like(hit_loc)
+        self.ctx._ck(self.L.drt_eval_texture(self.ctx.h, shader_serial, hit_loc.shape[0], hit_loc.ctypes.data, fwd_loc.ctypes.data, out.ctypes.data))
+        return out
+
+    def dump_bvh(self, top_index):
+        box = np.zeros(6)
+        n = self.L.drt_dump_bvh(self.ctx.h, top_index, None, 0, box.ctypes.data)
+        if n < 0:
+            return None, None
+        out = np.zeros(n, dtype=np.int32)
+        self.L.drt_dump_bvh(self.ctx.h, top_index, out.ctypes.data, n, box.ctypes.data)
+        return out, box
+
+    def obj_ctm(self, top_index):
+        m = np.zeros(16)
+        self.ctx._ck(self.L.drt_obj_ctm(self.ctx.h, top_index, m.ctypes.data))
+        return m.reshape(4, 4)
+
+
+class RTFileReader:
+    """myRTFileReader: reads a .cli file line by line, forwards every line, renders on `write`."""
+
+    def __init__(self, ctx, data_dir=SCENES_DIR, spp=0, photons=-1, accel=ACCEL_REFERENCE):
+        self.ctx, self.data_dir, self.spp, self.photons, self.accel = ctx, data_dir, spp, photons, accel
+        self.images = {}
+
+    def readRTFile(self, file_name, scene=None, out_dir=None):
+        main = scene is None
+        if main:
+            scene = Scene(self.ctx)
+        with open(os.path.join(self.data_dir, file_name)) as f:
+            for raw in f:
+                line = raw.rstrip("\r\n")
+                tok = [t for t in line.split(" ") if t]
+                if not tok or tok[0].startswith("#"):
+                    continue
+                if tok[0] == "read":
+                    self.readRTFile(tok[1], scene)
+                    continue
+                scene.command(line)
+                if tok[0] == "write":      # the reference renders inside the parser (myRTFileReader.java:86-93)
+                    scene.override(self.spp, self.photons)
+                    scene.finalize(self.accel)
+                    argb, st = scene.draw()
+                    self.images[tok[1]] = (argb, st)
+                    if out_dir:
+                        scene.save(os.path.join(out_dir, os.path.splitext(tok[1])[0] + ".png"), argb)
+        return scene
+
+
+def sample_u01(seed, stream, a, b, c, d):
+    return load_library().drt_sample_u01(seed, stream, a, b, c, d)

@@ -1,0 +1,84 @@
+/* drt.h -- C ABI of the B200 wavefront renderer that replaces the render path of
+ * jturner65/distRayTracer_old (package rayTracerDistAccelShdPhtnMap).
+ *
+ * The reference has no plugin/FFI seam; its render path sits behind
+ *   myRTFileReader.readRTFile()  (myRTFileReader.java:15-349, one switch per .cli line, `write` renders, :86-93)
+ *   myScene.initRender()/draw()  (myScene.java:1096-1099, :1481-1531, :1408-1443, :1589-1643, :1704-1753)
+ * whose only product is PImage.pixels (int ARGB, row-major, alpha 0xFF; myObjShader.java:671).
+ * A Java host binds these entry points through JNI or Panama FFM: the interpreter loop
+ * forwards every .cli line to drt_scene_command(), `write` calls drt_scene_finalize() + drt_render().
+ *
+ * Conventions: every function returns 0 on success or a negative drt_status; the message is available
+ * from drt_last_error(). There is NO CPU fallback: without a CUDA device drt_create fails with DRT_ERR_NO_DEVICE.
+ * One context is used by one host thread at a time (the reference is single threaded).
+ * The caller owns all input strings/arrays (copied during the call) and all output buffers.
+ */
+#ifndef DRT_H
+#define DRT_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct drt_ctx drt_ctx;
+
+typedef enum { DRT_OK = 0, DRT_ERR_NO_DEVICE = -1, DRT_ERR_BAD_ARG = -2, DRT_ERR_SCENE = -3, DRT_ERR_CUDA = -4, DRT_ERR_STATE = -5 } drt_status;
+
+/* acceleration-structure / traversal modes (drt_scene_finalize) */
+enum { DRT_ACCEL_REFERENCE = 0,   /* reference-topology BVH, reference traversal order and box rules (parity mode) */
+       DRT_ACCEL_REFERENCE_FAST = 1, /* same topology and hit rules, near-first ordered traversal with global pruning */
+       DRT_ACCEL_LBVH = 2 };      /* GPU-built 30-bit-Morton LBVH over triangle meshes (performance mode) */
+
+typedef struct drt_config {
+  int32_t device;          /* CUDA ordinal; < 0 = host-only context (interpret + flatten only, every render call fails) */
+  int32_t cols, rows;      /* output resolution (the reference hard-codes 300x300, DistRayTracer.java:15-16) */
+  int32_t counters;        /* !=0: count box / primitive tests (slower) */
+  uint64_t seed;           /* sampler seed (replaces the reference's unseeded ThreadLocalRandom) */
+  int64_t batch_rays;      /* primary rays per wavefront batch, 0 = default */
+} drt_config;
+
+typedef struct drt_stats {
+  uint64_t rays_primary, rays_shadow, rays_reflect, rays_refract, rays_photon;  /* logical rays, not the reference's copy count (myRay.java:30) */
+  uint64_t box_tests, prim_tests, photons_stored, kernel_launches;
+  double ms_trace, ms_shade, ms_light, ms_other, ms_total;                      /* CUDA-event times of the call */
+} drt_stats;
+
+/* host image decoder: PApplet.loadImage(name).pixels (myRTFileReader.java:133,265). Return 0 and fill w,h and a
+ * pointer to w*h ARGB ints that stays valid until the callback returns to the library (it copies). */
+typedef int (*drt_image_loader_fn)(void* user, const char* name, int32_t* w, int32_t* h, const int32_t** argb);
+
+int drt_create(const drt_config* cfg, drt_ctx** out);
+void drt_destroy(drt_ctx* ctx);
+const char* drt_last_error(drt_ctx* ctx);
+
+/* ---- scene description: replaces myRTFileReader.readRTFile + the myScene builders ---- */
+int drt_set_image_loader(drt_ctx* ctx, drt_image_loader_fn fn, void* user);
+int drt_set_texture_dir(drt_ctx* ctx, const char* dir);          /* fallback decoder cache: <dir>/<name>.argb */
+int drt_scene_reset(drt_ctx* ctx);                               /* new myFOVScene, fov 60 (myRTFileReader.java:27-28) */
+int drt_scene_command(drt_ctx* ctx, const char* line);           /* one .cli line (myRTFileReader.java:47-346) */
+int drt_scene_load_cli(drt_ctx* ctx, const char* file, const char* data_dir); /* whole file incl. nested `read` */
+int drt_scene_override(drt_ctx* ctx, int32_t spp, int64_t photons); /* <=0 / <0 keep the file's values */
+int drt_scene_finalize(drt_ctx* ctx, int32_t accel_mode);        /* flatten, build acceleration structures, upload to HBM */
+int drt_scene_reupload(drt_ctx* ctx);                            /* host->device copy of the flattened scene again (used by end-to-end timing) */
+int drt_scene_info(drt_ctx* ctx, int32_t* out16);                /* cols, rows, spp, top objects, lights, prims, instances, photon kind, shaders, nodes, xforms, lists, ... */
+
+/* ---- rendering: replaces myScene.initRender + draw; argb layout == PImage.pixels ---- */
+int drt_emit_photons(drt_ctx* ctx, drt_stats* stats);            /* myScene.sendCausticPhotons / sendDiffusePhotons (:952-1091) */
+int drt_render(drt_ctx* ctx, int32_t* argb_out, drt_stats* stats);                 /* host buffer, cols*rows */
+int drt_render_aov(drt_ctx* ctx, int32_t* argb_out, int32_t* hit_prim, int32_t* hit_inst, double* rgb, double* t, drt_stats* stats); /* any may be NULL */
+/* device-resident variant for multi-GPU hosts: render pixels [pix0,pix1) into caller-owned DEVICE buffers of cols*rows ints */
+int drt_render_device(drt_ctx* ctx, int64_t pix0, int64_t pix1, int32_t* argb_dev, drt_stats* stats);
+int drt_save_png(const char* path, const int32_t* argb, int32_t cols, int32_t rows);  /* PImage.save (myScene.java:1194) */
+
+/* ---- parity probes (used by tests; not needed by a host) ---- */
+int drt_trace_rays(drt_ctx* ctx, int64_t n, const double* org, const double* dir, int32_t* ids2, double* t);
+int drt_eval_texture(drt_ctx* ctx, int32_t shader_serial, int64_t n, const double* hit_loc, const double* fwd_loc, double* rgb);
+int64_t drt_dump_bvh(drt_ctx* ctx, int32_t top_index, int32_t* out, int64_t cap, double* root_box6);
+int drt_obj_ctm(drt_ctx* ctx, int32_t top_index, double* out16);
+double drt_sample_u01(uint64_t seed, uint32_t stream, uint32_t a, uint32_t b, uint32_t c, uint32_t d);
+int64_t drt_get_photons(drt_ctx* ctx, double* out6, int64_t cap);   /* x,y,z,r,g,b per stored photon */
+
+#ifdef __cplusplus
+}
+#endif
+#endif
