@@ -1,0 +1,246 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json): Mrays/s over all logical ray types and frame ms,
+bun69k 4K (3840x2160) 16 spp, on N B200s, beside the CPU restatement of the reference on the host cores.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one full frame of the workload through the wavefront kernels.
+  value    : whole-job throughput with the scene resident in HBM and the frame left on the device (tile gather included for N>1)
+  e2e      : same metric through the C ABI with HOST buffers: scene re-upload (H2D) + render + frame read-back (D2H) every step
+  roofline : dominant kernel (k_trace): algorithmic bytes touched per launch / CUDA-event duration vs the measured HBM copy peak
+  cpu_baseline : the oracle ("port" of the reference; the Java reference cannot run here) on a bounded tile of the same workload
+N>1: one process per GPU (torchrun), frame split in interleaved 8-row chunks (strong scaling: the frame is fixed), NCCL all-gather of chunks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(scene="p3_t09.cli", cols=3840, rows=2160, spp=16)
+METRIC = "Mrays/s (all ray types), bun69k 4K 16spp"
+CPU_TILE = (1728, 972, 1728 + 384, 972 + 216)      # bounded CPU sample: centre 384x216 tile of the 4K frame at 16 spp
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.stop, self.t = gpu, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True); self.t.start(); return self
+
+    def __exit__(self, *a):
+        self.stop = True; self.t.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_leg(threads, steps=1, warmup=0):
+    """Times the oracle (CPU restatement of the reference) on the bounded tile of the benchmark workload."""
+    from oracle import orc
+    orc.build()
+    w = WORKLOAD
+    o = orc.OracleScene(w["scene"], cols=w["cols"], rows=w["rows"], spp=w["spp"])
+    best = None
+    for i in range(warmup + steps):
+        r = o.render(rect=CPU_TILE, threads=threads, want=("argb",))
+        rays = sum(r["stats"][k] for k in ("primary", "shadow", "reflect", "refract"))
+        if i >= warmup and (best is None or r["seconds"] < best[0]):
+            best = (r["seconds"], rays)
+    return best[1] / best[0] / 1e6, best[0], best[1]
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # each step = the bounded tile, all host threads
+    from oracle import orc
+    orc.build()
+    w = WORKLOAD
+    o = orc.OracleScene(w["scene"], cols=w["cols"], rows=w["rows"], spp=w["spp"])
+    secs, rays = [], 0
+    for i in range(args.warmup + args.steps):
+        r = o.render(rect=CPU_TILE, threads=threads, want=("argb",))
+        if i >= args.warmup:
+            secs.append(r["seconds"]); rays = sum(r["stats"][k] for k in ("primary", "shadow", "reflect", "refract"))
+    ms = 1e3 * sum(secs) / len(secs)
+    value = rays / (ms / 1e3) / 1e6
+    sample = "oracle (C++ restatement of the Java reference; no JDK on the box), %d threads, tile x[%d,%d) y[%d,%d) of the 4K frame at 16 spp = %d rays per step" % (threads, CPU_TILE[0], CPU_TILE[2], CPU_TILE[1], CPU_TILE[3], rays)
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "%s %dx%d %dspp (bounded sample: centre 384x216 tile)" % (w["scene"], w["cols"], w["rows"], w["spp"])},
+                      "cpu_baseline": {"value": round(value, 4), "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
+                      "e2e": {"value": round(value, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--accel", type=int, default=int(os.environ.get("DRT_ACCEL", "0")))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import distraytracer_old_b200 as drt
+    from distraytracer_old_b200 import dist as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = WORKLOAD
+    ctx = drt.Context(device=local, cols=w["cols"], rows=w["rows"])
+    scene = drt.Scene.from_cli(ctx, w["scene"], spp=w["spp"], accel=args.accel)
+    npix = w["cols"] * w["rows"]
+    frame = torch.zeros(npix, dtype=torch.int32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        if world == 1:
+            st = scene.draw_device(0, npix, frame.data_ptr())
+            out = frame
+        else:
+            st = scene.draw_device_chunks(world, rank, D.CHUNK_ROWS, frame.data_ptr())
+            out = D.gather_frame(frame, w["rows"], w["cols"], world, rank, dist)
+        return st, out
+
+    for _ in range(args.warmup):
+        flush.fill_(1); step()
+    barrier()
+    gpu_ms, trace_ms, rays, launches, trace_launch_count = [], 0.0, 0, 0, 0
+    with ClockSampler(local) as cs:
+        for _ in range(args.steps):
+            flush.fill_(1)                       # L2 flush between timed iterations
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            st, out = step()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            t = torch.tensor([ms, float(st.rays_total), float(st.kernel_launches), st.ms_trace], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+                ms, r, l, tr = mx[0].item(), sm[1].item(), sm[2].item(), mx[3].item()
+            else:
+                r, l, tr = t[1].item(), t[2].item(), t[3].item()
+            gpu_ms.append(ms); rays = int(r); launches = int(l); trace_ms += tr
+    clocks = cs.summary()
+    ms_per_step = sum(gpu_ms) / len(gpu_ms)
+    value = rays / (ms_per_step / 1e3) / 1e6
+
+    # ---- e2e through the C ABI with host buffers (rank-local share for N>1 is not meaningful: measured at N==1 semantics on every rank's full frame)
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(npix, dtype=torch.int32).pin_memory()
+        scene_bytes = 0
+        info = scene.info()
+        scene_bytes = info["xforms"] * 384 + info["prims"] * 32 + info["nodes"] * 128 + info["lists"] * 64 + info["prims"] * 38 * 8
+        for _ in range(2):
+            scene.reupload(); scene.draw_into(host.data_ptr())
+        barrier(); t0 = time.perf_counter(); tot_r = 0
+        for _ in range(args.steps):
+            scene.reupload()                        # H2D of the flattened scene
+            st = scene.draw_into(host.data_ptr())   # kernels + D2H of the ARGB frame into pinned host memory
+            tot_r += st.rays_total
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        e2e_val = tot_r / dt / 1e6
+        if dist is not None:     # every rank rendered a full frame here; report the slowest rank's single-GPU figure
+            t = torch.tensor([e2e_val], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN); e2e_val = t.item() * world
+        e2e = {"value": round(e2e_val, 3), "unit": "Mrays/s", "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": npix * 4,
+               "note": "drt_scene_reupload + drt_render into pinned host memory, wall clock" + (" (N independent full frames)" if world > 1 else "")}
+
+    # ---- roofline of the dominant kernel (k_trace, primary level): algorithmic bytes touched per ray (SURVEY 8(d) form, this build's record sizes)
+    roof = None; cpu = None
+    if rank == 0:
+        peaks, which = measured_peaks()
+        cctx = drt.Context(device=local, cols=480, rows=270, counters=True)          # same camera/scene at 1/8 linear size: per-ray averages
+        cs2 = drt.Scene.from_cli(cctx, w["scene"], spp=w["spp"], accel=args.accel)
+        _, cst = cs2.draw()
+        r_all = cst.rays_primary + cst.rays_reflect + cst.rays_refract          # rays traced by k_trace (closest hit)
+        box_per_ray, prim_per_ray = cst.box_tests_closest / r_all, cst.prim_tests_closest / r_all
+        closest_share = r_all / cst.rays_total
+        cctx.close()
+        bytes_per_ray = 96 + 96 + 64 * box_per_ray + 104 * prim_per_ray               # ray rec in, hit rec out, 64 B per box (128 B node = 2 boxes), 104 B per triangle state
+        n_trace_launches = max(1, -(-(npix * w["spp"]) // (8 << 20)))                  # primary-level launches per step (one per batch)
+        ms_trace_step = trace_ms / len(gpu_ms)
+        closest_rays_per_step = rays * closest_share                                   # primary + reflection + refraction rays of one frame
+        achieved = closest_rays_per_step * bytes_per_ray / (ms_trace_step / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_trace", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
+                "traffic": None, "peak_source": which + " (burst copy)", "per_ray": {"box_tests": round(box_per_ray, 2), "prim_tests": round(prim_per_ray, 2), "bytes": round(bytes_per_ray, 1)},
+                "ms_trace_per_step": round(ms_trace_step, 3), "launches_per_step": n_trace_launches,
+                "note": "traversal is issue/latency bound with an L2-resident scene (SURVEY 8(d)); bytes are algorithmic bytes touched, not DRAM traffic; see profiles/ for ncu dram bytes and issue-slot utilisation"}
+        tr_path = os.path.join(ROOT, "profiles", "trace_traffic.json")
+        if os.path.exists(tr_path):
+            try:
+                roof["traffic"] = json.load(open(tr_path)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu:
+            v, secs, crays = cpu_leg(1)
+            cpu = {"value": round(v, 4), "unit": "Mrays/s", "cores": 1, "kind": "port",
+                   "sample": "oracle (C++ restatement; the Java reference has no JDK here), single thread like the reference, centre 384x216 tile of the 4K/16spp frame: %d rays in %.1f s" % (crays, secs)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 3), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%s %dx%d %dspp (configs[1]: bun69k in the p3_t09 wrapper; mesh = bun500 subdivided 3x, 61824 tris, stand-in for the missing bun69k.cli)" % (w["scene"], w["cols"], w["rows"], w["spp"]),
+                           "accel": ["reference-topology literal", "reference-topology fast", "lbvh"][args.accel], "l2": "flushed between timed iterations (256 MiB fill)", "partition": "interleaved 8-row chunks" if world > 1 else "single GPU",
+                           "rays_per_frame": rays},
+                "frame_ms": round(ms_per_step, 3), "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,7 +30,7 @@ struct drt_ctx {
 static void toStats(const RenderStats& r, drt_stats* s) {
   if (!s) return;
   s->rays_primary = r.primary; s->rays_shadow = r.shadow; s->rays_reflect = r.reflect; s->rays_refract = r.refract; s->rays_photon = r.photonSeg;
-  s->box_tests = r.boxTests; s->prim_tests = r.primTests; s->photons_stored = r.photonsStored; s->kernel_launches = r.kernelLaunches;
+  s->box_tests = r.boxTests; s->prim_tests = r.primTests; s->photons_stored = r.photonsStored; s->kernel_launches = r.kernelLaunches; s->box_tests_closest = r.boxTestsClosest; s->prim_tests_closest = r.primTestsClosest;
   s->ms_trace = r.msTrace; s->ms_shade = r.msShade; s->ms_light = r.msLight; s->ms_other = r.msOther; s->ms_total = r.msTotal;
 }
 #define NEED_DEV(ctx) if ((ctx) && !(ctx)->renderer) { (ctx)->err = "host-only context: no CUDA device, and this library has no CPU fallback"; return DRT_ERR_NO_DEVICE; }
@@ -68,7 +68,7 @@ int drt_scene_finalize(drt_ctx* ctx, int32_t accel_mode) {
 }
 int drt_scene_reupload(drt_ctx* ctx) { NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized) throw std::runtime_error("scene not finalized"); ctx->renderer->upload(*ctx->scene); }, DRT_ERR_STATE) }
 int drt_scene_info(drt_ctx* ctx, int32_t* o) {
-  GUARD(ctx, { const HostScene& s = *ctx->scene; std::memset(o, 0, 16 * sizeof(int32_t));
+  GUARD(ctx, { ctx->scene->finalize(); const HostScene& s = *ctx->scene; std::memset(o, 0, 16 * sizeof(int32_t));
     o[0] = s.g.cols; o[1] = s.g.rows; o[2] = s.g.spp; o[3] = (int)s.top.size(); o[4] = (int)s.lights.size(); o[5] = (int)s.prims.size(); o[6] = (int)s.instances.size(); o[7] = s.g.photonKind;
     o[8] = (int)s.shaders.size(); o[9] = (int)s.nodes.size(); o[10] = (int)s.xforms.size(); o[11] = (int)s.lists.size(); o[12] = (int)s.bvhs.size(); o[13] = (int)s.images.size(); o[14] = (int)s.warnings.size(); o[15] = s.g.numPhotonsCast; }, DRT_ERR_SCENE)
 }
@@ -81,6 +81,12 @@ int drt_render(drt_ctx* ctx, int32_t* argb, drt_stats* stats) { return drt_rende
 int drt_render_device(drt_ctx* ctx, int64_t pix0, int64_t pix1, int32_t* argb_dev, drt_stats* stats) {
   NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized) throw std::runtime_error("scene not finalized"); RenderStats rs; std::memset(&rs, 0, sizeof(rs)); RenderOutputs o; std::memset(&o, 0, sizeof(o)); o.argb = argb_dev;
     ctx->renderer->renderRange(pix0, pix1, o, &rs); toStats(rs, stats); }, DRT_ERR_CUDA)
+}
+
+int drt_render_device_chunks(drt_ctx* ctx, int32_t world, int32_t rank, int32_t chunk_rows, int32_t* argb_dev, drt_stats* stats) {
+  NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized) throw std::runtime_error("scene not finalized"); if (world < 1 || rank < 0 || rank >= world || chunk_rows < 1) throw std::runtime_error("bad partition");
+    RenderStats rs; std::memset(&rs, 0, sizeof(rs)); RenderOutputs o; std::memset(&o, 0, sizeof(o)); o.argb = argb_dev;
+    ctx->renderer->renderChunks(0, 0, world, rank, chunk_rows, o, &rs); toStats(rs, stats); }, DRT_ERR_CUDA)
 }
 
 // PNG (8-bit RGB, zlib deflate) -- PImage.save of an RGB image

@@ -516,14 +516,6 @@ void HostScene::finalize() {
   top.clear();
   for (const HGeom& gm : topGeoms_) { FObjRef r; r.kind = gm.kind; r.idx = gm.idx; r.xform = gm.xform; r.hitXform = gm.xform; top.push_back(r); }
   g.numTop = (int)top.size(); g.numLights = (int)lights.size();
-  // nesting supported on the device: top -> {prim, instance(prim|accel), accel}; accel child -> {prim, instance(prim|accel of prims)}
-  for (const FInstance& in : instances) {
-    if (in.baseKind == OK_LIST || in.baseKind == OK_BVH) {
-      std::vector<int> ls;
-      if (in.baseKind == OK_LIST) ls.push_back(in.baseIdx);
-      // children of an instanced accel may themselves be instances of accels only one level deep; checked at traversal build
-    }
-  }
 }
 
 void HostScene::dumpNode(int32_t ref, std::vector<int32_t>& out) const {

@@ -24,7 +24,11 @@ struct alignas(16) RayRec { double o[3], d[3]; double kt0, kt1; uint32_t ka, kb,
 struct alignas(16) SurfRec { double loc[3], n[3], rawDir[3], tex[3]; int32_t shader, valid; uint32_t ka, kb, kc, stream; int32_t gen, pad; };
 struct alignas(16) NodeRec { double local[3], cA[3], cB[3], w[3]; int32_t parent, slot; int32_t pad[2]; };
 
-struct Counters { unsigned long long primary, shadow, reflect, refract, box, prim, nextCount, pad; };
+// compact pixel index -> absolute pixel (row-major). Identity for single-GPU; interleaved row chunks for multi-GPU tiles.
+struct PixMap { long long chunkPix, totalPix; int world, rank; };
+__host__ __device__ __forceinline__ long long absPixel(const PixMap& m, long long p) { return ((p / m.chunkPix) * m.world + m.rank) * m.chunkPix + (p % m.chunkPix); }
+
+struct Counters { unsigned long long primary, shadow, reflect, refract, box, prim, nextCount, boxC, primC, pad; };
 
 __device__ __forceinline__ void warpAdd(unsigned long long* dst, unsigned long long v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -32,15 +36,15 @@ __device__ __forceinline__ void warpAdd(unsigned long long* dst, unsigned long l
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DScene S, long long pix0, long long nRays, RayRec* __restrict__ rays, NodeRec* __restrict__ nodes) {
+__global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DScene S, PixMap pm, long long pix0, long long nRays, RayRec* __restrict__ rays, NodeRec* __restrict__ nodes) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= nRays) return;
   const FGlobals& g = S.g; int spp = g.spp < 1 ? 1 : g.spp;
-  long long pix = pix0 + i / spp; uint32_t smp = (uint32_t)(i % spp);
+  long long pix = absPixel(pm, pix0 + i / spp); uint32_t smp = (uint32_t)(i % spp);
   int row = (int)(pix / g.cols), col = (int)(pix % g.cols);
   RayRec r; r.kt0 = 1; r.kt1 = 1; r.ka = (uint32_t)pix; r.kb = smp; r.kc = 1; r.stream = STREAM_PIXEL; r.gen = 0; r.valid = 1; r.pad[0] = r.pad[1] = 0;
   D3 o = d3(g.eye[0], g.eye[1], g.eye[2]), d = d3(0, 0, -1);
   auto U = [&](uint32_t dim) { return philoxU01(g.seed, STREAM_PIXEL, (uint32_t)pix, smp, 1, dim); };
-  if (g.spp < 1) r.valid = 0;     // rays_per_pixel 0: the reference averages nothing (0/0 -> NaN -> 0)
+  if (g.spp < 1 || pix >= pm.totalPix) r.valid = 0;     // rays_per_pixel 0: the reference averages nothing (0/0 -> NaN -> 0); ragged last chunk
   if (g.camKind == CAM_FOV) {
     double rayY = (-1 * (row - g.rayYOffset)), rayX = col - g.rayXOffset;
     if (g.hasDof) {
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(128) k_trace(const __grid_constant__ DScene S,
     }
     hits[i] = h;
   }
-  if (COUNT) { warpAdd(&ctr->box, tc.box); warpAdd(&ctr->prim, tc.prim); }
+  if (COUNT) { warpAdd(&ctr->box, tc.box); warpAdd(&ctr->prim, tc.prim); warpAdd(&ctr->boxC, tc.box); warpAdd(&ctr->primC, tc.prim); }
 }
 
 // skydome lookup for rays that leave the scene (myScene.java:1104-1149): nearest texel, no filtering
@@ -251,14 +255,14 @@ __global__ void k_resolve(long long n, const NodeRec* __restrict__ lvl, NodeRec*
   double* dst = (nd.slot == 1) ? parentLvl[nd.parent].cA : parentLvl[nd.parent].cB;
   dst[0] = nd.w[0] * c.x; dst[1] = nd.w[1] * c.y; dst[2] = nd.w[2] * c.z;
 }
-__global__ void k_finish(const __grid_constant__ DScene S, long long pix0, long long nPix, const NodeRec* __restrict__ roots, const Hit* __restrict__ hits0, RenderOutputs out) {
+__global__ void k_finish(const __grid_constant__ DScene S, PixMap pm, long long pix0, long long nPix, const NodeRec* __restrict__ roots, const Hit* __restrict__ hits0, RenderOutputs out) {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (p >= nPix) return;
+  long long q = absPixel(pm, pix0 + p); if (q >= pm.totalPix) return;
   int spp = S.g.spp < 1 ? 1 : S.g.spp; double r = 0, g = 0, b = 0;
   for (int s = 0; s < spp; ++s) { D3 c = nodeTotal(roots[p * spp + s]); r += c.x; g += c.y; b += c.z; }
   D3 c;
   if (S.g.spp < 1) c = d3(0, 0, 0);
   else c = clampColor1(d3(r / spp, g / spp, b / spp));
-  long long q = pix0 + p;
   if (out.argb) out.argb[q] = packArgb(c);
   if (out.rgb) { out.rgb[3 * q] = c.x; out.rgb[3 * q + 1] = c.y; out.rgb[3 * q + 2] = c.z; }
   if (out.hitPrim || out.hitInst || out.t) {
@@ -369,8 +373,14 @@ void Renderer::upload(const HostScene& hs) {
 
 static inline unsigned gridFor(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
-void Renderer::renderRange(long long pix0, long long pix1, const RenderOutputs& out, RenderStats* stats) {
+void Renderer::renderRange(long long pix0, long long pix1, const RenderOutputs& out, RenderStats* stats) { renderChunks(pix0, pix1, 1, 0, 0, out, stats); }
+
+// world > 1: compact pixel p of this rank maps to interleaved row chunks (chunkRows rows each, chunk c of the rank = absolute chunk c*world+rank)
+void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank, int chunkRows, const RenderOutputs& out, RenderStats* stats) {
   CK(cudaSetDevice(device_)); cudaStream_t st = (cudaStream_t)stream_; Impl& I = *impl_;
+  PixMap pm; pm.totalPix = (long long)g_.cols * g_.rows; pm.world = world < 1 ? 1 : world; pm.rank = rank;
+  pm.chunkPix = (pm.world == 1) ? (pm.totalPix > 0 ? pm.totalPix : 1) : (long long)chunkRows * g_.cols;
+  if (pm.world > 1) { long long nChunks = (g_.rows + chunkRows - 1) / chunkRows, mine = (nChunks - rank + world - 1) / world; pix0 = 0; pix1 = mine * pm.chunkPix; }
   if (!I.ds.prims) throw std::runtime_error("render called before a scene was uploaded");
   if (g_.photonKind != 0 && !I.photons.built) { I.photons.emitAndBuild(I.ds, st, stats); }
   const int spp = g_.spp < 1 ? 1 : g_.spp;
@@ -384,7 +394,7 @@ void Renderer::renderRange(long long pix0, long long pix1, const RenderOutputs& 
     CK(cudaMemsetAsync(I.ctr, 0, sizeof(Counters), st));
     std::vector<long long> lvlCount, lvlOff; long long n = n0, off = 0; int cur = 0;
     I.rays[0].ensure(n0, st); I.nodes.ensure(n0, st, false); I.hits0.ensure(n0, st);
-    k_raygen<<<gridFor(n0, 256), 256, 0, st>>>(I.ds, b0, n0, I.rays[0].p, I.nodes.p); ++rs.kernelLaunches;
+    k_raygen<<<gridFor(n0, 256), 256, 0, st>>>(I.ds, pm, b0, n0, I.rays[0].p, I.nodes.p); ++rs.kernelLaunches;
     for (int level = 0; n > 0; ++level) {
       lvlCount.push_back(n); lvlOff.push_back(off);
       Hit* hitBuf; if (level == 0) hitBuf = I.hits0.p; else { I.hits.ensure(n, st); hitBuf = I.hits.p; }
@@ -411,10 +421,10 @@ void Renderer::renderRange(long long pix0, long long pix1, const RenderOutputs& 
     for (int level = (int)lvlCount.size() - 1; level >= 1; --level) {
       k_resolve<<<gridFor(lvlCount[level], 256), 256, 0, st>>>(lvlCount[level], I.nodes.p + lvlOff[level], I.nodes.p + lvlOff[level - 1]); ++rs.kernelLaunches;
     }
-    k_finish<<<gridFor(nPix, 256), 256, 0, st>>>(I.ds, b0, nPix, I.nodes.p, I.hits0.p, out); ++rs.kernelLaunches;
+    k_finish<<<gridFor(nPix, 256), 256, 0, st>>>(I.ds, pm, b0, nPix, I.nodes.p, I.hits0.p, out); ++rs.kernelLaunches;
     CK(cudaMemcpyAsync(I.ctrHost, I.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    rs.primary += I.ctrHost->primary; rs.shadow += I.ctrHost->shadow; rs.reflect += I.ctrHost->reflect; rs.refract += I.ctrHost->refract; rs.boxTests += I.ctrHost->box; rs.primTests += I.ctrHost->prim;
+    rs.primary += I.ctrHost->primary; rs.shadow += I.ctrHost->shadow; rs.reflect += I.ctrHost->reflect; rs.refract += I.ctrHost->refract; rs.boxTests += I.ctrHost->box; rs.primTests += I.ctrHost->prim; rs.boxTestsClosest += I.ctrHost->boxC; rs.primTestsClosest += I.ctrHost->primC;
   }
   CK(cudaEventRecord(I.ev[5], st)); CK(cudaStreamSynchronize(st));
   float tot; CK(cudaEventElapsedTime(&tot, I.ev[0], I.ev[5]));

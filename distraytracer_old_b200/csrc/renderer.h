@@ -7,7 +7,7 @@ namespace drt {
 
 struct RenderStats {
   unsigned long long primary, shadow, reflect, refract, photonSeg;   // logical rays
-  unsigned long long boxTests, primTests;                           // only when counters are enabled
+  unsigned long long boxTests, primTests, boxTestsClosest, primTestsClosest;   // only when counters are enabled
   unsigned long long photonsStored;
   unsigned long long kernelLaunches;
   double msTrace, msShade, msLight, msOther, msTotal;               // CUDA-event times of the last render call
@@ -27,6 +27,7 @@ class Renderer {
   void setTraceMode(int m) { traceMode_ = m; }
   // render pixels [pix0, pix1) (row-major pixel indices) into the device buffers of `out` (indexed by absolute pixel)
   void renderRange(long long pix0, long long pix1, const RenderOutputs& out, RenderStats* stats);
+  void renderChunks(long long pix0, long long pix1, int world, int rank, int chunkRows, const RenderOutputs& out, RenderStats* stats);
   // full frame to host memory (D2H inside)
   void renderToHost(int32_t* argbHost, int32_t* hitPrimHost, int32_t* hitInstHost, double* rgbHost, double* tHost, RenderStats* stats);
   // explicit world-space rays (closest hit only) for parity tests: ids = {primSerial, instSerial} per ray

@@ -24,7 +24,7 @@ class _Config(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays_primary", "rays_shadow", "rays_reflect", "rays_refract", "rays_photon",
-                                           "box_tests", "prim_tests", "photons_stored", "kernel_launches")] + \
+                                           "box_tests", "prim_tests", "photons_stored", "kernel_launches", "box_tests_closest", "prim_tests_closest")] + \
                [(n, C.c_double) for n in ("ms_trace", "ms_shade", "ms_light", "ms_other", "ms_total")]
 
     def as_dict(self):
@@ -71,6 +71,7 @@ def load_library():
         "drt_render": (C.c_int, [vp, vp, C.POINTER(Stats)]),
         "drt_render_aov": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(Stats)]),
         "drt_render_device": (C.c_int, [vp, i64, i64, vp, C.POINTER(Stats)]),
+        "drt_render_device_chunks": (C.c_int, [vp, i32, i32, i32, vp, C.POINTER(Stats)]),
         "drt_save_png": (C.c_int, [C.c_char_p, vp, i32, i32]),
         "drt_trace_rays": (C.c_int, [vp, i64, vp, vp, vp, vp]),
         "drt_eval_texture": (C.c_int, [vp, i32, i64, vp, vp, vp]),
@@ -89,7 +90,7 @@ def load_library():
 
 EXPORTS = ["drt_create", "drt_destroy", "drt_last_error", "drt_set_image_loader", "drt_set_texture_dir", "drt_scene_reset",
            "drt_scene_command", "drt_scene_load_cli", "drt_scene_override", "drt_scene_finalize", "drt_scene_reupload",
-           "drt_scene_info", "drt_emit_photons", "drt_render", "drt_render_aov", "drt_render_device", "drt_save_png",
+           "drt_scene_info", "drt_emit_photons", "drt_render", "drt_render_aov", "drt_render_device", "drt_render_device_chunks", "drt_save_png",
            "drt_trace_rays", "drt_eval_texture", "drt_dump_bvh", "drt_obj_ctm", "drt_sample_u01", "drt_get_photons"]
 
 
@@ -209,6 +210,11 @@ class Scene:
     def draw_device(self, pix0, pix1, dev_ptr):
         st = Stats()
         self.ctx._ck(self.L.drt_render_device(self.ctx.h, pix0, pix1, dev_ptr, C.byref(st)))
+        return st
+
+    def draw_device_chunks(self, world, rank, chunk_rows, dev_ptr):
+        st = Stats()
+        self.ctx._ck(self.L.drt_render_device_chunks(self.ctx.h, world, rank, chunk_rows, dev_ptr, C.byref(st)))
         return st
 
     def emit_photons(self):

@@ -40,6 +40,7 @@ typedef struct drt_config {
 typedef struct drt_stats {
   uint64_t rays_primary, rays_shadow, rays_reflect, rays_refract, rays_photon;  /* logical rays, not the reference's copy count (myRay.java:30) */
   uint64_t box_tests, prim_tests, photons_stored, kernel_launches;
+  uint64_t box_tests_closest, prim_tests_closest;                                 /* the closest-hit (k_trace) share of the two counters above */
   double ms_trace, ms_shade, ms_light, ms_other, ms_total;                      /* CUDA-event times of the call */
 } drt_stats;
 
@@ -68,6 +69,9 @@ int drt_render(drt_ctx* ctx, int32_t* argb_out, drt_stats* stats);              
 int drt_render_aov(drt_ctx* ctx, int32_t* argb_out, int32_t* hit_prim, int32_t* hit_inst, double* rgb, double* t, drt_stats* stats); /* any may be NULL */
 /* device-resident variant for multi-GPU hosts: render pixels [pix0,pix1) into caller-owned DEVICE buffers of cols*rows ints */
 int drt_render_device(drt_ctx* ctx, int64_t pix0, int64_t pix1, int32_t* argb_dev, drt_stats* stats);
+/* multi-GPU tiles: render this rank's interleaved row chunks (chunk c of the rank = rows [(c*world+rank)*chunk_rows, +chunk_rows)) at their
+ * absolute positions of a full cols*rows DEVICE buffer; pixels of other ranks are left untouched */
+int drt_render_device_chunks(drt_ctx* ctx, int32_t world, int32_t rank, int32_t chunk_rows, int32_t* argb_dev, drt_stats* stats);
 int drt_save_png(const char* path, const int32_t* argb, int32_t cols, int32_t rows);  /* PImage.save (myScene.java:1194) */
 
 /* ---- parity probes (used by tests; not needed by a host) ---- */

@@ -132,7 +132,7 @@ class OracleScene:
         out = np.zeros_like(hit_loc)
         r = lib().orc_eval_texture(self.h, shader_serial, hit_loc.shape[0], hit_loc.ctypes.data, fwd_loc.ctypes.data, out.ctypes.data)
         if r != 0:
-            raise IndexError("no such shader")
+            raise IndexError("no such shader" if r == -1 else "image textures cannot be probed")
         return out
 
     def obj_ctm(self, idx):

@@ -117,6 +117,7 @@ long long orc_dump_bvh(void* hv, int objIdx, int32_t* out, long long cap, double
 int orc_eval_texture(void* hv, int serial, long long n, const double* hitLoc, const double* fwdLoc, double* out) {
   Scene* s = ((OrcHandle*)hv)->get(0); if (serial < 0 || serial >= (int)s->allShaders.size()) return -1;
   Shader* sh = s->allShaders[serial];
+  if (sh->txtr->topImage()) return -2;   // image textures need a primitive for (u,v); probe procedural textures only
   for (long long i = 0; i < n; ++i) {
     RayHit h; h.isHit = true; h.hitLoc = Vec3(hitLoc[3 * i], hitLoc[3 * i + 1], hitLoc[3 * i + 2]); h.fwdTransHitLoc = Vec3(fwdLoc[3 * i], fwdLoc[3 * i + 1], fwdLoc[3 * i + 2]);
     sh->txtr->getDiffTxtrColor(h, sh->diffuseColor, sh->simple ? 1.0 : sh->diffConst, out + 3 * i);
