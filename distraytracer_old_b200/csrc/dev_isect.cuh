@@ -16,14 +16,23 @@ namespace drt {
 // origin, "direction" vector (may be re-normalised in place), "dirAra" copy (never re-normalised) -- myRay.java:14-18
 struct Ray { D3 o, d, a; bool norm; };
 
-struct Hit {
+struct alignas(16) Hit {
   double t;
   int32_t prim, arg0, arg1, state;        // state: polygon winding state used (0/1[/2 for planes])
-  int32_t hitXform, shaderOverride, inst;
+  int32_t hitXform, shaderOverride, inst, pad0;
   D3 loc;                                  // hit point in the primitive's space (rayHit.hitLoc)
   D3 rawDir;                               // rayHit.fwdTransRayDir
+  double pad1;
 };
-__device__ __forceinline__ void hitReset(Hit& h) { h.t = DRT_DMAX; h.prim = -1; h.arg0 = 0; h.arg1 = 0; h.state = 0; h.hitXform = -1; h.shaderOverride = -1; h.inst = -1; }
+// what a primitive test reports; the caller fills the Hit record only for candidates that win
+struct PHit { double t; int32_t arg0, arg1, state, boxRaw; };
+__device__ __forceinline__ void takeHit(const DScene& S, Hit& dst, const PHit& ph, int primIdx, const Ray& r, D3 rawDir, int hitXform) {
+  dst.t = ph.t; dst.prim = primIdx; dst.arg0 = ph.arg0; dst.arg1 = ph.arg1; dst.state = ph.state; dst.hitXform = hitXform; dst.shaderOverride = -1; dst.inst = -1;
+  dst.loc = d3((r.d.x * ph.t) + r.o.x, (r.d.y * ph.t) + r.o.y, (r.d.z * ph.t) + r.o.z);       // transRay.pointOnRay(t), myRay.java:82-87
+  // rendered box: the direction recorded in the hit is CTM x transformed direction (myGeomBase.java:160)
+  dst.rawDir = ph.boxRaw ? xfVector(S.xforms[S.prims[primIdx].xform].m, r.d) : rawDir;
+}
+__device__ __forceinline__ void hitReset(Hit& h) { h.t = DRT_DMAX; h.prim = -1; h.arg0 = 0; h.arg1 = 0; h.state = 0; h.hitXform = -1; h.shaderOverride = -1; h.inst = -1; h.pad0 = 0; h.loc = d3(0, 0, 0); h.rawDir = d3(0, 0, 0); h.pad1 = 0; }
 
 struct TraceCounters { unsigned long long box, prim; };
 
@@ -55,7 +64,8 @@ __device__ __forceinline__ bool boxTest(const double* __restrict__ mn, const dou
 
 // ---- primitives. `r` is the ray in the primitive's space, rawDir the direction recorded in the hit.
 // Returns true and fills h (t, loc, args, state) on a hit. time: ray time for moving spheres.
-__device__ __noinline__ bool primTest(const DScene& S, int primIdx, const Ray& r, D3 rawDir, double time, Hit& h) {
+__device__ __noinline__ bool primTest(const DScene& S, int primIdx, const Ray& r, double time, PHit& h) {
+  h.boxRaw = 0;
   const FPrim P = S.prims[primIdx];
   const double* __restrict__ q = S.pdata + P.data;
   switch (P.type) {
@@ -72,7 +82,7 @@ __device__ __noinline__ bool primTest(const DScene& S, int primIdx, const Ray& r
         double d1 = sqrt(discr), t1 = (-1 * b + d1) / (ta), t2 = (-1 * b - d1) / (ta);
         double tv = jminD(t1, t2);
         if (tv < DRT_EPS) { tv = jmaxD(t1, t2); if (tv < DRT_EPS) return false; }
-        h.t = tv; h.loc = pointOnRay(r, tv); h.prim = primIdx; h.arg0 = 0; h.arg1 = 0; h.state = 0; h.rawDir = rawDir; return true;
+        h.t = tv; h.arg0 = 0; h.arg1 = 0; h.state = 0; return true;
       }
       return false;
     }
@@ -97,7 +107,7 @@ __device__ __noinline__ bool primTest(const DScene& S, int primIdx, const Ray& r
         D3 tmp = cross3(ir, e);
         if (dot3(tmp, N) < -DRT_EPS) return false;
       }
-      h.t = t; h.loc = p; h.prim = primIdx; h.arg0 = 0; h.arg1 = 0; h.state = st; h.rawDir = rawDir; return true;
+      h.t = t; h.arg0 = 0; h.arg1 = 0; h.state = st; return true;
     }
     case PT_PLANE: {
       int st = 0; D3 N = d3(q[0], q[1], q[2]); double D = q[3];
@@ -107,7 +117,7 @@ __device__ __noinline__ bool primTest(const DScene& S, int primIdx, const Ray& r
         if (planeRes > 0) { st = 2; N = d3(q[8], q[9], q[10]); D = q[11]; planeRes = dot3(N, r.d); if (!(fabs(planeRes) > 0) || planeRes > 0) return false; } }
       double t = -(dot3(N, r.o) + D) / planeRes;
       if (!(t > DRT_EPS)) return false;
-      h.t = t; h.loc = pointOnRay(r, t); h.prim = primIdx; h.arg0 = 0; h.arg1 = 0; h.state = st; h.rawDir = rawDir; return true;
+      h.t = t; h.arg0 = 0; h.arg1 = 0; h.state = st; return true;
     }
     case PT_HCYL: {
       double cx = q[0], cz = q[2], radX = q[3], radZ = q[4], yTop = q[5], yBot = q[6];
@@ -119,9 +129,9 @@ __device__ __noinline__ bool primTest(const DScene& S, int primIdx, const Ray& r
         double tv = jminD(t1, t2), to = jmaxD(t1, t2);
         if (tv < -DRT_EPS) { double tmp = to; to = tv; tv = tmp; if (tv < -DRT_EPS) return false; }
         double y1 = r.o.y + (tv * r.d.y);
-        if ((tv > DRT_EPS) && (y1 > yBot) && (y1 < yTop)) { h.t = tv; h.loc = pointOnRay(r, tv); h.prim = primIdx; h.arg0 = 0; h.arg1 = 0; h.state = 0; h.rawDir = rawDir; return true; }
+        if ((tv > DRT_EPS) && (y1 > yBot) && (y1 < yTop)) { h.t = tv; h.arg0 = 0; h.arg1 = 0; h.state = 0; return true; }
         double y2 = r.o.y + (to * r.d.y);
-        if ((to > DRT_EPS) && (y2 > yBot) && (y2 < yTop)) { h.t = to; h.loc = pointOnRay(r, to); h.prim = primIdx; h.arg0 = 1; h.arg1 = 0; h.state = 0; h.rawDir = rawDir; return true; }
+        if ((to > DRT_EPS) && (y2 > yBot) && (y2 < yTop)) { h.t = to; h.arg0 = 1; h.arg1 = 0; h.state = 0; return true; }
       }
       return false;
     }
@@ -146,15 +156,13 @@ __device__ __noinline__ bool primTest(const DScene& S, int primIdx, const Ray& r
         double tv, mxC = jmaxD(cv, co), mnC = jminD(cv, co);
         if (planeRes && (((mnC <= 0) && (pv >= -DRT_EPS) && (pv <= mxC)) || ((pv > mnC) && (pv <= mxC)))) tv = pv; else { tv = cv; vis = 2; }
         double y1 = r.o.y + (tv * r.d.y);
-        if ((y1 + DRT_EPS >= yBot) && (y1 - DRT_EPS <= yTop)) { h.t = tv; h.loc = pointOnRay(r, tv); h.prim = primIdx; h.arg0 = vis; h.arg1 = 0; h.state = 0; h.rawDir = rawDir; return true; }
+        if ((y1 + DRT_EPS >= yBot) && (y1 - DRT_EPS <= yTop)) { h.t = tv; h.arg0 = vis; h.arg1 = 0; h.state = 0; return true; }
       }
       return false;
     }
     case PT_BOX: {
       double t; int face; if (!boxTest(q, q + 3, r, t, face)) return false;
-      // rendered box: ray direction recorded in the hit is CTM x transformed direction (myGeomBase.java:160)
-      h.t = t; h.loc = pointOnRay(r, t); h.prim = primIdx; h.arg0 = 0; h.arg1 = face; h.state = 0;
-      h.rawDir = xfVector(S.xforms[P.xform].m, r.d); return true;
+      h.t = t; h.arg0 = 0; h.arg1 = face; h.state = 0; h.boxRaw = 1; return true;
     }
   }
   return false;
@@ -180,15 +188,22 @@ __device__ __forceinline__ double leafClosest(const DScene& S, int listIdx, Ray&
   for (int i = 0; i < L.childCount; ++i) {
     const FObjRef c = S.children[L.childStart + i];
     Ray r = xfRay(_ray, S.xforms[c.xform].inv);
-    Hit h; hitReset(h); bool got = false;
-    if (c.kind == OK_PRIM) { if (tc) ++tc->prim; got = primTest(S, c.idx, r, _ray.d, time, h); }
-    else {   // instance: the already transformed ray is forwarded as both rays (mySceneObject.java:123-127)
+    if (c.kind == OK_PRIM) {
+      PHit ph; if (tc) ++tc->prim;
+      if (primTest(S, c.idx, r, time, ph) && ph.t < clsT) { clsT = ph.t; takeHit(S, res, ph, c.idx, r, _ray.d, c.hitXform); }
+    } else {   // instance: the already transformed ray is forwarded as both rays (mySceneObject.java:123-127)
       const FInstance I = S.instances[c.idx];
-      if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; got = primTest(S, I.baseIdx, r, r.d, time, h); }
-      else if (LVL == 1) got = accelClosest<2>(S, I.baseKind, I.baseIdx, r, r, time, h, tc);
-      if (got) { if (I.shader >= 0) h.shaderOverride = I.shader; if (h.inst < 0) h.inst = I.serial; }
+      if (I.baseKind == OK_PRIM) {
+        PHit ph; if (tc) ++tc->prim;
+        if (primTest(S, I.baseIdx, r, time, ph) && ph.t < clsT) { clsT = ph.t; takeHit(S, res, ph, I.baseIdx, r, r.d, c.hitXform); if (I.shader >= 0) res.shaderOverride = I.shader; res.inst = I.serial; }
+      } else if (LVL == 1) {
+        Hit h; hitReset(h);
+        if (accelClosest<2>(S, I.baseKind, I.baseIdx, r, r, time, h, tc) && h.t < clsT) {
+          clsT = h.t; res.t = h.t; res.prim = h.prim; res.arg0 = h.arg0; res.arg1 = h.arg1; res.state = h.state; res.loc = h.loc; res.rawDir = h.rawDir;
+          res.hitXform = c.hitXform; res.shaderOverride = (I.shader >= 0) ? I.shader : h.shaderOverride; res.inst = (h.inst < 0) ? I.serial : h.inst;
+        }
+      }
     }
-    if (got && h.t < clsT) { clsT = h.t; res = h; res.hitXform = c.hitXform; }
   }
   return clsT;
 }
@@ -205,22 +220,23 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
     const FList& L = S.lists[idx];
     if (tc) ++tc->box;
     if (!boxTest(L.bmin, L.bmax, trans, te, face)) return false;
-    Hit h; hitReset(h); double t = leafClosest<LVL>(S, idx, _ray, time, h, tc);
-    if (t < DRT_DMAX) { out = h; return true; }
-    return false;
+    double t = leafClosest<LVL>(S, idx, _ray, time, out, tc);
+    return t < DRT_DMAX;
   }
   const FBvh& B = S.bvhs[idx];
   if (tc) ++tc->box;
   if (!boxTest(B.bmin, B.bmax, trans, te, face)) return false;
-  Hit best; hitReset(best);
+  Hit& best = out; hitReset(best);
+  Hit leaf; hitReset(leaf);
   Frame stack[DRT_STACK]; int sp = 0;
   int32_t node = B.root; double tCur = DRT_DMAX;
   while (true) {
     bool ret = false;
     int32_t afterLeftOf = -1;
     if (node < 0) {                    // leaf
-      Hit h; hitReset(h); tCur = leafClosest<LVL>(S, ~node, _ray, time, h, tc);
-      if (h.t < best.t) best = h;
+      tCur = leafClosest<LVL>(S, ~node, _ray, time, leaf, tc);
+      if (tCur < best.t) { best.t = leaf.t; best.prim = leaf.prim; best.arg0 = leaf.arg0; best.arg1 = leaf.arg1; best.state = leaf.state; best.hitXform = leaf.hitXform;
+        best.shaderOverride = leaf.shaderOverride; best.inst = leaf.inst; best.loc = leaf.loc; best.rawDir = leaf.rawDir; }
       ret = true;
     } else {
       const FNode& N = S.nodes[node];
@@ -237,7 +253,7 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
         afterLeftOf = -1; ret = true;  // result of this node = tL (an untraversed right box can never win: te >= tL)
       }
       if (ret) {
-        if (sp == 0) { if (best.t < DRT_DMAX) { out = best; return true; } return false; }
+        if (sp == 0) return best.t < DRT_DMAX;
         --sp;
         if (stack[sp].node >= 0) { afterLeftOf = stack[sp].node; continue; }
         double tL = stack[sp].tL; tCur = (tL <= tCur) ? tL : tCur;       // min, left wins ties
@@ -250,18 +266,29 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
 // myScene.findClosestRayHit: linear scan of the top-level list, first-inserted wins among equal t
 __device__ __forceinline__ bool closestHit(const DScene& S, Ray& ray, double time, Hit& best, TraceCounters* tc) {
   hitReset(best);
+  Hit h; hitReset(h);
   for (int i = 0; i < S.g.numTop; ++i) {
     const FObjRef o = S.top[i];
     Ray tr = xfRay(ray, S.xforms[o.xform].inv);
-    Hit h; hitReset(h); bool got = false;
-    if (o.kind == OK_PRIM) { if (tc) ++tc->prim; got = primTest(S, o.idx, tr, ray.d, time, h); if (got) h.hitXform = o.xform; }
-    else if (o.kind == OK_INSTANCE) {
-      const FInstance I = S.instances[o.idx];
-      if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; got = primTest(S, I.baseIdx, tr, tr.d, time, h); if (got) h.hitXform = o.xform; }
-      else got = accelClosest<1>(S, I.baseKind, I.baseIdx, tr, tr, time, h, tc);
-      if (got) { if (I.shader >= 0) h.shaderOverride = I.shader; if (h.inst < 0) h.inst = I.serial; }
-    } else got = accelClosest<1>(S, o.kind, o.idx, ray, tr, time, h, tc);
-    if (got && h.t < best.t) best = h;
+    if (o.kind == OK_PRIM) {
+      PHit ph; if (tc) ++tc->prim;
+      if (primTest(S, o.idx, tr, time, ph) && ph.t < best.t) takeHit(S, best, ph, o.idx, tr, ray.d, o.xform);
+    } else {
+      bool got; int shader = -1, serial = -1;
+      if (o.kind == OK_INSTANCE) {
+        const FInstance I = S.instances[o.idx]; shader = I.shader; serial = I.serial;
+        if (I.baseKind == OK_PRIM) {
+          PHit ph; if (tc) ++tc->prim;
+          if (primTest(S, I.baseIdx, tr, time, ph) && ph.t < best.t) { takeHit(S, best, ph, I.baseIdx, tr, tr.d, o.xform); if (shader >= 0) best.shaderOverride = shader; best.inst = serial; }
+          continue;
+        }
+        got = accelClosest<1>(S, I.baseKind, I.baseIdx, tr, tr, time, h, tc);
+      } else got = accelClosest<1>(S, o.kind, o.idx, ray, tr, time, h, tc);
+      if (got && h.t < best.t) {
+        best.t = h.t; best.prim = h.prim; best.arg0 = h.arg0; best.arg1 = h.arg1; best.state = h.state; best.hitXform = h.hitXform; best.loc = h.loc; best.rawDir = h.rawDir;
+        best.shaderOverride = (shader >= 0) ? shader : h.shaderOverride; best.inst = (serial >= 0 && h.inst < 0) ? serial : h.inst;
+      }
+    }
   }
   return best.t < DRT_DMAX;
 }
@@ -282,11 +309,11 @@ __device__ __forceinline__ bool listShadow(const DScene& S, int listIdx, Ray& _r
   for (int i = 0; i < L.childCount; ++i) {
     const FObjRef c = S.children[L.childStart + i];
     Ray r = xfRay(_ray, S.xforms[c.xform].inv);
-    Hit h; hitReset(h);
-    if (c.kind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, c.idx, r, _ray.d, time, h) && (dist - h.t) > DRT_EPS) return true; }
+    PHit h;
+    if (c.kind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, c.idx, r, time, h) && (dist - h.t) > DRT_EPS) return true; }
     else {
       const FInstance I = S.instances[c.idx];
-      if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, I.baseIdx, r, r.d, time, h) && (dist - h.t) > DRT_EPS) return true; }
+      if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, I.baseIdx, r, time, h) && (dist - h.t) > DRT_EPS) return true; }
       else if (LVL == 1) { if (accelShadow<2>(S, I.baseKind, I.baseIdx, r, r, time, dist, tc)) return true; }
     }
   }
@@ -316,11 +343,11 @@ __device__ __forceinline__ bool anyHit(const DScene& S, Ray& ray, double time, d
   for (int i = 0; i < S.g.numTop; ++i) {
     const FObjRef o = S.top[i];
     Ray tr = xfRay(ray, S.xforms[o.xform].inv);
-    Hit h; hitReset(h);
-    if (o.kind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, o.idx, tr, ray.d, time, h) && (dist - h.t) > DRT_EPS) return true; }
+    PHit h;
+    if (o.kind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, o.idx, tr, time, h) && (dist - h.t) > DRT_EPS) return true; }
     else if (o.kind == OK_INSTANCE) {
       const FInstance I = S.instances[o.idx];
-      if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, I.baseIdx, tr, tr.d, time, h) && (dist - h.t) > DRT_EPS) return true; }
+      if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, I.baseIdx, tr, time, h) && (dist - h.t) > DRT_EPS) return true; }
       else if (accelShadow<1>(S, I.baseKind, I.baseIdx, tr, tr, time, dist, tc)) return true;
     } else if (accelShadow<1>(S, o.kind, o.idx, ray, tr, time, dist, tc)) return true;
   }

@@ -274,10 +274,13 @@ __global__ void k_finish(const __grid_constant__ DScene S, PixMap pm, long long 
 }
 
 // parity helpers ------------------------------------------------------------------------------------------------
+template <bool COUNT>
 __global__ void k_trace_explicit(const __grid_constant__ DScene S, long long n, const double* __restrict__ org, const double* __restrict__ dir, int32_t* __restrict__ ids, double* __restrict__ tOut) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
   Ray ray = makeRay(d3(org[3 * i], org[3 * i + 1], org[3 * i + 2]), norm3(d3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2])));
-  Hit h; closestHit(S, ray, 0.0, h, nullptr);
+  TraceCounters tc; tc.box = 0; tc.prim = 0;
+  Hit h; closestHit(S, ray, 0.0, h, COUNT ? &tc : nullptr);
+  if (COUNT && tc.box == 0xFFFFFFFFFFFFull) ids[0] = 0;
   ids[2 * i] = h.prim >= 0 ? S.prims[h.prim].serial : -1; ids[2 * i + 1] = h.prim >= 0 ? h.inst : -1; tOut[i] = h.prim >= 0 ? h.t : 0;
 }
 __global__ void k_eval_texture(const __grid_constant__ DScene S, int shader, long long n, const double* __restrict__ hl, const double* __restrict__ fl, double* __restrict__ out) {
@@ -401,12 +404,12 @@ void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank,
       I.surf.ensure(n, st);
       long long nextCap = 2 * n; I.rays[cur ^ 1].ensure(nextCap, st); I.nodes.ensure(off + n + nextCap, st, true);
       CK(cudaEventRecord(I.ev[1], st));
-      if (counters_) k_trace<true><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.rays[cur].p, hitBuf, I.ctr);
+      if (counters_ || (traceMode_ & 512)) k_trace<true><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.rays[cur].p, hitBuf, I.ctr);
       else k_trace<false><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.rays[cur].p, hitBuf, I.ctr);
       CK(cudaEventRecord(I.ev[2], st));
       k_shade<<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.rays[cur].p, hitBuf, I.surf.p, I.nodes.p + off, I.rays[cur ^ 1].p, I.nodes.p + off + n, I.ctr, nextCap);
       CK(cudaEventRecord(I.ev[3], st));
-      if (counters_) k_light<true><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off, I.ctr);
+      if (counters_ || (traceMode_ & 256)) k_light<true><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off, I.ctr);
       else k_light<false><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off, I.ctr);
       CK(cudaEventRecord(I.ev[4], st));
       rs.kernelLaunches += 3;
@@ -439,6 +442,10 @@ void Renderer::renderToHost(int32_t* argbHost, int32_t* hitPrimHost, int32_t* hi
   if (argbHost) { I.oArgb.ensure(np, st); o.argb = I.oArgb.p; } if (hitPrimHost) { I.oPrim.ensure(np, st); o.hitPrim = I.oPrim.p; }
   if (hitInstHost) { I.oInst.ensure(np, st); o.hitInst = I.oInst.p; } if (rgbHost) { I.oRgb.ensure(3 * np, st); o.rgb = I.oRgb.p; } if (tHost) { I.oT.ensure(np, st); o.t = I.oT.p; }
   renderRange(0, (long long)np, o, stats);
+  if (const char* dump = getenv("DRT_DUMP_HITS")) {   // debugging aid
+    std::vector<Hit> hh(np * (g_.spp < 1 ? 1 : g_.spp)); CK(cudaMemcpy(hh.data(), I.hits0.p, hh.size() * sizeof(Hit), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(dump, "wb"); if (f) { fwrite(hh.data(), sizeof(Hit), hh.size(), f); fclose(f); }
+  }
   if (argbHost) CK(cudaMemcpyAsync(argbHost, o.argb, np * 4, cudaMemcpyDeviceToHost, st));
   if (hitPrimHost) CK(cudaMemcpyAsync(hitPrimHost, o.hitPrim, np * 4, cudaMemcpyDeviceToHost, st));
   if (hitInstHost) CK(cudaMemcpyAsync(hitInstHost, o.hitInst, np * 4, cudaMemcpyDeviceToHost, st));
@@ -459,7 +466,8 @@ void Renderer::traceRays(long long n, const double* orgHost, const double* dirHo
   CK(cudaSetDevice(device_)); cudaStream_t st = (cudaStream_t)stream_;
   double *o, *d, *t; int32_t* ids; CK(cudaMalloc(&o, n * 24)); CK(cudaMalloc(&d, n * 24)); CK(cudaMalloc(&t, n * 8)); CK(cudaMalloc(&ids, n * 8));
   CK(cudaMemcpyAsync(o, orgHost, n * 24, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(d, dirHost, n * 24, cudaMemcpyHostToDevice, st));
-  k_trace_explicit<<<gridFor(n, 128), 128, 0, st>>>(impl_->ds, n, o, d, ids, t);
+  if (counters_) k_trace_explicit<true><<<gridFor(n, 128), 128, 0, st>>>(impl_->ds, n, o, d, ids, t);
+  else k_trace_explicit<false><<<gridFor(n, 128), 128, 0, st>>>(impl_->ds, n, o, d, ids, t);
   CK(cudaMemcpyAsync(idsHost, ids, n * 8, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(tHost, t, n * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
   cudaFree(o); cudaFree(d); cudaFree(t); cudaFree(ids);

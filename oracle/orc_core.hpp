@@ -205,9 +205,12 @@ struct Planar : Geom {
     return true;
   }
   RayHit intersectCheck(Ray& _ray, Ray& tr, CTM* ct) override;       // :104-115
-  Vec3 getNormalAtPoint(const Vec3&, const int*) override {          // :130-136
-    st[cur].N.normalize();
-    Vec3 res = st[cur].N;
+  Vec3 getNormalAtPoint(const Vec3&, const int*) override;           // :130-136
+  Vec3 getNormalAtPointImpl(bool literal) {
+    // the reference normalises N itself (`res = N; res._normalize()` aliases), so N drifts by an ulp after the first hit;
+    // canonical mode normalises a copy so that hit decisions do not depend on the order rays were traced in
+    Vec3 res = st[cur].N; res.normalize();
+    if (literal) st[cur].N = res;
     if (inverted) { invertNormal(); res = st[cur].N; res.normalize(); }
     return res;
   }

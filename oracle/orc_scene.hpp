@@ -246,6 +246,7 @@ inline RayHit Geom::objHit(const Ray& tr, const Vec3& rawRayDir, CTM* ct, const 
   return h;
 }
 
+inline Vec3 Planar::getNormalAtPoint(const Vec3&, const int*) { return getNormalAtPointImpl(scene->opt.literalRenorm); }
 inline RayHit RndrdBox::intersectCheck(Ray&, Ray& tr, CTM* ct) {
   double t; int idx; if (!bbox.test(tr, t, idx, scene->stats)) return RayHit();
   int args[2] = {0, idx};

@@ -7,7 +7,7 @@ import distraytracer_old_b200 as drt
 from oracle import orc
 
 def compare(name, cols=300, rows=300, spp=0, photons=-1, accel=0, save=None):
-    ctx = drt.Context(device=0, cols=cols, rows=rows, counters=True)
+    ctx = drt.Context(device=0, cols=cols, rows=rows, counters=os.environ.get("DRT_COUNTERS", "1") == "1")
     t0 = time.time(); s = drt.Scene.from_cli(ctx, name, spp=spp, photons=photons, accel=accel); tl = time.time() - t0
     g = s.draw(aov=True); g2 = s.draw(aov=True)
     o = orc.OracleScene(name, cols=cols, rows=rows, spp=spp if spp > 0 else -1, photons=photons)
