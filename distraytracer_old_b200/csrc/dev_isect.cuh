@@ -62,6 +62,32 @@ __device__ __forceinline__ bool boxTest(const double* __restrict__ mn, const dou
   return false;
 }
 
+// Same decisions and the same entry t as boxTest(), bit for bit, at a fraction of the FP64 divisions:
+// the six slab values are first formed with a per-ray reciprocal (<= 2 ulp from the quotient the reference computes);
+// every comparison the reference makes (v1<v2 per axis, min(tMax) > max(tMin), entry > 0, which tMin is largest) is accepted
+// only when the operands are separated by far more than that error; the one value that leaves the function (entry t) is then
+// recomputed with the reference's own division.  Anything closer than the margin falls back to the literal test.
+#define DRT_CLEAR(a, b) (fabs((a) - (b)) > 1e-14 * (fabs(a) + fabs(b)))
+__device__ __forceinline__ bool boxTestFx(const double* __restrict__ mn, const double* __restrict__ mx, const Ray& r, const D3& inv, double& tEntry) {
+  const double nx1 = mn[0] - r.o.x, nx2 = mx[0] - r.o.x, ny1 = mn[1] - r.o.y, ny2 = mx[1] - r.o.y, nz1 = mn[2] - r.o.z, nz2 = mx[2] - r.o.z;
+  const double ax1 = nx1 * inv.x, ax2 = nx2 * inv.x, ay1 = ny1 * inv.y, ay2 = ny2 * inv.y, az1 = nz1 * inv.z, az2 = nz2 * inv.z;
+  const bool sx = ax1 < ax2, sy = ay1 < ay2, sz = az1 < az2;
+  const double tnx = sx ? ax1 : ax2, tfx = sx ? ax2 : ax1, tny = sy ? ay1 : ay2, tfy = sy ? ay2 : ay1, tnz = sz ? az1 : az2, tfz = sz ? az2 : az1;
+  double far_ = tfx; if (tfy < far_) far_ = tfy; if (tfz < far_) far_ = tfz;
+  double near_ = tnx; int ax = 0; if (tny > near_) { near_ = tny; ax = 1; } if (tnz > near_) { near_ = tnz; ax = 2; }
+  const double second = (ax == 0) ? (tny > tnz ? tny : tnz) : (ax == 1 ? (tnx > tnz ? tnx : tnz) : (tnx > tny ? tnx : tny));
+  // all operands finite and every decision clear of the reciprocal's error?
+  const bool ok = DRT_CLEAR(ax1, ax2) && DRT_CLEAR(ay1, ay2) && DRT_CLEAR(az1, az2) && DRT_CLEAR(far_, near_) && DRT_CLEAR(near_, second) && (fabs(near_) > 1e-290) && (fabs(far_) < 1e290) && (fabs(near_) < 1e290);
+  if (!ok) { int face; return boxTest(mn, mx, r, tEntry, face); }
+  if (!((far_ > near_) && near_ > 0)) return false;
+  // entry t exactly as the reference forms it: (bound - origin) / direction on the winning axis
+  const double num = (ax == 0) ? (sx ? nx1 : nx2) : (ax == 1 ? (sy ? ny1 : ny2) : (sz ? nz1 : nz2));
+  const double den = (ax == 0) ? r.a.x : (ax == 1 ? r.a.y : r.a.z);
+  tEntry = num / den;
+  return true;
+}
+__device__ __forceinline__ D3 rayInv(const Ray& r) { return d3(1.0 / r.a.x, 1.0 / r.a.y, 1.0 / r.a.z); }
+
 // ---- primitives. `r` is the ray in the primitive's space, rawDir the direction recorded in the hit.
 // Returns true and fills h (t, loc, args, state) on a hit. time: ray time for moving spheres.
 __device__ __noinline__ bool primTest(const DScene& S, int primIdx, const Ray& r, double time, PHit& h) {
@@ -171,7 +197,7 @@ __device__ __noinline__ bool primTest(const DScene& S, int primIdx, const Ray& r
 #define DRT_STACK 48
 struct Frame { int32_t node; double tL; };     // node >= 0: "after left" of that node; node == -1: "after right", tL saved
 
-template <int LVL> struct Lvl {};
+struct XfCache;
 
 // ---------------------------------------------------------------------------------------------------------------
 // closest hit
@@ -181,13 +207,19 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
 
 // myGeomList.traverseStruct: every child gets a fresh transform of `_ray`; first strictly smaller t wins;
 // the winner's CTM becomes list.CTM x child.CTM (child.hitXform).
+// children of one mesh normally share one CTM: the transformed ray is a pure function of (_ray, xform), so it is kept
+struct XfCache { int xf; Ray r; };
+__device__ __forceinline__ const Ray& xfRayCached(const DScene& S, Ray& _ray, int xf, XfCache& xc) {
+  if (xc.xf != xf) { xc.r = xfRay(_ray, S.xforms[xf].inv); xc.xf = xf; }
+  return xc.r;
+}
 template <int LVL>
-__device__ __forceinline__ double leafClosest(const DScene& S, int listIdx, Ray& _ray, double time, Hit& res, TraceCounters* tc) {
+__device__ __forceinline__ double leafClosest(const DScene& S, int listIdx, Ray& _ray, double time, Hit& res, TraceCounters* tc, XfCache& xc) {
   const FList L = S.lists[listIdx];
   double clsT = DRT_DMAX;
   for (int i = 0; i < L.childCount; ++i) {
     const FObjRef c = S.children[L.childStart + i];
-    Ray r = xfRay(_ray, S.xforms[c.xform].inv);
+    Ray r = xfRayCached(S, _ray, c.xform, xc);
     if (c.kind == OK_PRIM) {
       PHit ph; if (tc) ++tc->prim;
       if (primTest(S, c.idx, r, time, ph) && ph.t < clsT) { clsT = ph.t; takeHit(S, res, ph, c.idx, r, _ray.d, c.hitXform); }
@@ -220,12 +252,15 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
     const FList& L = S.lists[idx];
     if (tc) ++tc->box;
     if (!boxTest(L.bmin, L.bmax, trans, te, face)) return false;
-    double t = leafClosest<LVL>(S, idx, _ray, time, out, tc);
+    XfCache xc; xc.xf = -1;
+    double t = leafClosest<LVL>(S, idx, _ray, time, out, tc, xc);
     return t < DRT_DMAX;
   }
   const FBvh& B = S.bvhs[idx];
   if (tc) ++tc->box;
   if (!boxTest(B.bmin, B.bmax, trans, te, face)) return false;
+  const D3 inv = rayInv(trans);
+  XfCache xc; xc.xf = -1;
   Hit& best = out; hitReset(best);
   Hit leaf; hitReset(leaf);
   Frame stack[DRT_STACK]; int sp = 0;
@@ -234,21 +269,21 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
     bool ret = false;
     int32_t afterLeftOf = -1;
     if (node < 0) {                    // leaf
-      tCur = leafClosest<LVL>(S, ~node, _ray, time, leaf, tc);
+      tCur = leafClosest<LVL>(S, ~node, _ray, time, leaf, tc, xc);
       if (tCur < best.t) { best.t = leaf.t; best.prim = leaf.prim; best.arg0 = leaf.arg0; best.arg1 = leaf.arg1; best.state = leaf.state; best.hitXform = leaf.hitXform;
         best.shaderOverride = leaf.shaderOverride; best.inst = leaf.inst; best.loc = leaf.loc; best.rawDir = leaf.rawDir; }
       ret = true;
     } else {
       const FNode& N = S.nodes[node];
       if (tc) ++tc->box;
-      if (boxTest(N.lmin, N.lmax, trans, te, face) && sp < DRT_STACK) { stack[sp].node = node; stack[sp].tL = 0; ++sp; node = N.left; tCur = DRT_DMAX; continue; }
+      if (boxTestFx(N.lmin, N.lmax, trans, inv, te) && sp < DRT_STACK) { stack[sp].node = node; stack[sp].tL = 0; ++sp; node = N.left; tCur = DRT_DMAX; continue; }
       tCur = DRT_DMAX; afterLeftOf = node;
     }
     while (true) {
       if (afterLeftOf >= 0) {          // left subtree of `afterLeftOf` finished with tCur
         const FNode& N = S.nodes[afterLeftOf];
         if (tc) ++tc->box;
-        bool hr = boxTest(N.rmin, N.rmax, trans, te, face);
+        bool hr = boxTestFx(N.rmin, N.rmax, trans, inv, te);
         if (hr && (!(tCur < DRT_DMAX) || te < tCur) && sp < DRT_STACK) { stack[sp].node = -1; stack[sp].tL = tCur; ++sp; node = N.right; tCur = DRT_DMAX; ret = false; break; }
         afterLeftOf = -1; ret = true;  // result of this node = tL (an untraversed right box can never win: te >= tL)
       }
@@ -301,14 +336,14 @@ template <int LVL>
 __device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc);
 
 template <int LVL>
-__device__ __forceinline__ bool listShadow(const DScene& S, int listIdx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc) {
+__device__ __forceinline__ bool listShadow(const DScene& S, int listIdx, Ray& _ray, const Ray& trans, const D3& inv, double time, double dist, TraceCounters* tc, XfCache& xc) {
   const FList L = S.lists[listIdx];
-  double te; int face;
+  double te;
   if (tc) ++tc->box;
-  if (!(boxTest(L.bmin, L.bmax, trans, te, face) && (dist - te) > DRT_EPS)) return false;
+  if (!(boxTestFx(L.bmin, L.bmax, trans, inv, te) && (dist - te) > DRT_EPS)) return false;
   for (int i = 0; i < L.childCount; ++i) {
     const FObjRef c = S.children[L.childStart + i];
-    Ray r = xfRay(_ray, S.xforms[c.xform].inv);
+    Ray r = xfRayCached(S, _ray, c.xform, xc);
     PHit h;
     if (c.kind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, c.idx, r, time, h) && (dist - h.t) > DRT_EPS) return true; }
     else {
@@ -321,17 +356,19 @@ __device__ __forceinline__ bool listShadow(const DScene& S, int listIdx, Ray& _r
 }
 template <int LVL>
 __device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc) {
-  if (kind == OK_LIST) return listShadow<LVL>(S, idx, _ray, trans, time, dist, tc);
+  const D3 inv = rayInv(trans);
+  XfCache xc; xc.xf = -1;
+  if (kind == OK_LIST) return listShadow<LVL>(S, idx, _ray, trans, inv, time, dist, tc, xc);
   const FBvh& B = S.bvhs[idx];
   int32_t stack[DRT_STACK]; int sp = 0; int32_t node = B.root;
-  double te; int face;
+  double te;
   while (true) {
-    if (node < 0) { if (listShadow<LVL>(S, ~node, _ray, trans, time, dist, tc)) return true; }
+    if (node < 0) { if (listShadow<LVL>(S, ~node, _ray, trans, inv, time, dist, tc, xc)) return true; }
     else {
       const FNode& N = S.nodes[node];
       if (tc) tc->box += 2;
-      bool hl = boxTest(N.lmin, N.lmax, trans, te, face) && (dist - te) > DRT_EPS;
-      bool hr = boxTest(N.rmin, N.rmax, trans, te, face) && (dist - te) > DRT_EPS;
+      bool hl = boxTestFx(N.lmin, N.lmax, trans, inv, te) && (dist - te) > DRT_EPS;
+      bool hr = boxTestFx(N.rmin, N.rmax, trans, inv, te) && (dist - te) > DRT_EPS;
       if (hl) { if (hr && sp < DRT_STACK) stack[sp++] = N.right; node = N.left; continue; }
       if (hr) { node = N.right; continue; }
     }

@@ -83,8 +83,14 @@ __device__ __forceinline__ double rayTime(const DScene& S, uint32_t stream, uint
   return S.g.pad0 ? philoxU01(S.g.seed, stream, a, b, c, dim) : 0.0;      // pad0 = scene has moving spheres
 }
 
+#ifndef DRT_TRACE_MINBLOCKS
+#define DRT_TRACE_MINBLOCKS 6
+#endif
+#ifndef DRT_LIGHT_MINBLOCKS
+#define DRT_LIGHT_MINBLOCKS 6
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace(const __grid_constant__ DScene S, long long n, const RayRec* __restrict__ rays, Hit* __restrict__ hits, Counters* ctr) {
+__global__ void __launch_bounds__(128, DRT_TRACE_MINBLOCKS) k_trace(const __grid_constant__ DScene S, long long n, const RayRec* __restrict__ rays, Hit* __restrict__ hits, Counters* ctr) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   TraceCounters tc; tc.box = 0; tc.prim = 0;
   if (i < n) {
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene S,
 
 // Light pass: literal calcShadowColor, one thread per shaded hit, lights in list order, shadow rays traced in-thread.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_light(const __grid_constant__ DScene S, long long n, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, Counters* ctr) {
+__global__ void __launch_bounds__(128, DRT_LIGHT_MINBLOCKS) k_light(const __grid_constant__ DScene S, long long n, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, Counters* ctr) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   TraceCounters tc; tc.box = 0; tc.prim = 0; unsigned long long cShadow = 0;
   if (i < n) {

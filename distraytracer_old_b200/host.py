@@ -41,7 +41,7 @@ _lib = None
 
 
 def lib_path():
-    return os.path.join(HERE, "libdrt.so")
+    return os.environ.get("DRT_LIB") or os.path.join(HERE, "libdrt.so")     # DRT_LIB: tuning variants built by tools/, never a fallback
 
 
 def load_library():
