@@ -74,6 +74,10 @@ int drt_scene_info(drt_ctx* ctx, int32_t* o) {
 }
 
 int drt_emit_photons(drt_ctx* ctx, drt_stats* stats) { NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized) throw std::runtime_error("scene not finalized"); RenderStats rs; std::memset(&rs, 0, sizeof(rs)); ctx->renderer->emitPhotons(&rs); toStats(rs, stats); }, DRT_ERR_CUDA) }
+int drt_emit_photons_range(drt_ctx* ctx, int64_t i0, int64_t i1, drt_stats* stats) { NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized) throw std::runtime_error("scene not finalized"); RenderStats rs; std::memset(&rs, 0, sizeof(rs)); ctx->renderer->emitPhotonsRange(i0, i1, &rs); toStats(rs, stats); }, DRT_ERR_CUDA) }
+int64_t drt_photons_export_device(drt_ctx* ctx, double* dst, int64_t cap) { if (!ctx) return DRT_ERR_BAD_ARG; NEED_DEV(ctx) try { return ctx->renderer->exportPhotonsDevice(dst, cap); } catch (std::exception& e) { ctx->err = e.what(); return DRT_ERR_CUDA; } }
+int drt_photons_build_device(drt_ctx* ctx, const double* src, int64_t n, drt_stats* stats) { NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized) throw std::runtime_error("scene not finalized"); RenderStats rs; std::memset(&rs, 0, sizeof(rs)); ctx->renderer->buildPhotonsFromDevice(src, n, &rs); toStats(rs, stats); }, DRT_ERR_CUDA) }
+int drt_photon_probe(drt_ctx* ctx, int64_t n, const double* pts, double* out5) { NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized) throw std::runtime_error("scene not finalized"); if (n < 0 || !pts || !out5) throw std::runtime_error("bad probe buffers"); ctx->renderer->probePhotons(n, pts, out5); }, DRT_ERR_CUDA) }
 int drt_render_aov(drt_ctx* ctx, int32_t* argb, int32_t* hp, int32_t* hi, double* rgb, double* t, drt_stats* stats) {
   NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized) throw std::runtime_error("scene not finalized"); RenderStats rs; std::memset(&rs, 0, sizeof(rs)); ctx->renderer->renderToHost(argb, hp, hi, rgb, t, &rs); toStats(rs, stats); }, DRT_ERR_CUDA)
 }

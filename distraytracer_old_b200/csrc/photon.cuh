@@ -1,12 +1,418 @@
-// Photon map: emission + trace kernel, hash-grid build, kNN radiance gather (filled in below).
+// Photon map on the device: emission + random-walk kernel, uniform-grid build (cell count -> scan -> stable radix sort),
+// warp-cooperative k-nearest radiance gather.
+//
+// Replaces (reference file:line, /root/reference/src/rayTracerDistAccelShdPhtnMap/):
+//   k_photon_emit     myScene.java:952-998 sendCausticPhotons, :1000-1091 sendDiffusePhotons (one thread = one emitted photon,
+//                     the whole walk of <= numPhotonRays+1 segments in-thread); myLight.java:59-74 getRandDir, :104-107 / :165-185 /
+//                     :229-242 genRndPhtnRay; myObjShader.java:461-478 findCausticRayHit, :297-406 calcTransRay / calcReflRay
+//   grid build        myLight.java:325-381 myKD_Tree.build_tree (balanced kd-tree) -> uniform grid of cell size >= search radius;
+//                     photons sorted by cell with the stable radix sort of dev_sort.cuh, cellStart = exclusive scan of per-cell counts
+//   k_photon_gather   myLight.java:389-445 find_near (k nearest with d^2 < r^2, shrinking radius) + myObjShader.java:441-458
+//                     getIrradianceFromPhtnTree: sum(power) / (PI_float * d^2 of the farthest of the k).  The set "k nearest inside the
+//                     radius" does not depend on the search structure, so the grid returns what the kd-tree returns (exact-distance
+//                     ties at the k-th neighbour excepted).
+// Photon order is canonical: record order = (photon index, light index, store index), independent of launch geometry and of how
+// photon indices are split across GPUs; the per-cell order after the stable sort inherits it, so sums are reproducible.
 #pragma once
+#include "dev_sort.cuh"
+#include <algorithm>
+#include <vector>
+
 namespace drt {
-struct PhotonMap {
-  bool built = false; unsigned long long count = 0;
-  void reset() { built = false; count = 0; }
-  void release() {}
-  long long download(double* out6, long long cap, cudaStream_t st) { (void)out6; (void)cap; (void)st; return 0; }
-  void emitAndBuild(DScene& ds, cudaStream_t st, RenderStats* stats) { (void)ds; (void)st; (void)stats; built = true; }
+
+struct alignas(16) PhotonRec { double x, y, z, r, g, b; };     // 48 B: position (world) + power
+
+// ---------------------------------------------------------------------------------------------------------------
+// emission
+// ---------------------------------------------------------------------------------------------------------------
+struct PhSampler {
+  uint64_t seed; uint32_t photon, light;
+  __device__ __forceinline__ double u(uint32_t seg, uint32_t dim) const { return philoxU01(seed, STREAM_PHOTON, photon, light, seg, dim); }
 };
-__device__ D3 photonIrradiance(const DScene& S, D3 p) { (void)S; (void)p; return d3(0, 0, 0); }
+
+// Light::getRandDir: rejection-sampled uniform direction (myLight.java:59-74)
+__device__ inline D3 phRandDir(const PhSampler& sp, uint32_t& draw) {
+  double x, y, z, sq;
+  do {
+    x = urange(sp.u(0, draw), -1.0, 1.0); y = urange(sp.u(0, draw + 1), -1.0, 1.0); z = urange(sp.u(0, draw + 2), -1.0, 1.0); draw += 3;
+    sq = (x * x) + (y * y) + (z * z);
+  } while ((sq > 1.0) || (sq < DRT_EPS));
+  double mag = sqrt(sq); return d3(x / mag, y / mag, z / mag);
+}
+__device__ __forceinline__ double phAngleProb(double angle, double inner, double outer, double diff) { return (angle < inner) ? 1 : (angle > outer) ? 0 : (outer - angle) / diff; }
+
+__device__ inline void phGenRay(const DScene& S, const FLight& L, const PhSampler& sp, D3& org, D3& dir) {
+  uint32_t draw = 0; const FXform& LX = S.xforms[L.xform];
+  D3 lo = d3(L.origin[0], L.origin[1], L.origin[2]), orient = d3(L.orient[0], L.orient[1], L.orient[2]), tang = d3(L.tangent[0], L.tangent[1], L.tangent[2]);
+  if (L.type == LT_POINT) { dir = phRandDir(sp, draw); org = xfPoint(LX.m, lo); }
+  else if (L.type == LT_SPOT) {
+    double prob, angle, checkProb = urange(sp.u(0, draw++), 0, 1);
+    do { angle = urange(sp.u(0, draw++), 0, L.outerRad); prob = phAngleProb(angle, L.innerRad, L.outerRad, L.radDiff); } while (prob > checkProb);
+    D3 tmp = norm3(rotAboutAxis(orient, tang, angle));
+    dir = rotAboutAxis(tmp, orient, urange(sp.u(0, draw++), 0, DRT_TWO_PI_F)); org = xfPoint(LX.m, lo);
+  } else {
+    double prob, angle;
+    do { angle = urange(sp.u(0, draw), 0, DRT_PI); prob = phAngleProb(angle, 0, DRT_PI, DRT_PI); double chk = urange(sp.u(0, draw + 1), 0, 1); draw += 2; if (!(prob > chk)) break; } while (true);
+    D3 d = norm3(rotAboutAxis(orient, tang, angle));
+    d = rotAboutAxis(d, orient, urange(sp.u(0, draw), 0, DRT_TWO_PI_F));
+    double ua = sp.u(0, draw + 1), ur = sp.u(0, draw + 2); draw += 3;
+    D3 tmp = norm3(rotAboutAxis(tang, orient, urange(ua, 0, DRT_TWO_PI_F)));
+    dir = d; org = xfPoint(LX.m, add3(scale3(tmp, urange(ur, 0, L.radius)), lo));
+  }
+}
+
+struct PhHit { bool isHit; int shader; int gen; uint32_t seg; double kt0; D3 fwd, nrm, rawDir; };
+__device__ __noinline__ void phTrace(const DScene& S, D3 o, D3 dirUnnormalized, int gen, uint32_t seg, double kt0, const PhSampler& sp, PhHit& ph) {
+  Ray ray = makeRay(o, norm3(dirUnnormalized)); Hit h;
+  double time = S.g.pad0 ? sp.u(seg, 0xFFFFu) : 0.0;
+  ph.isHit = closestHit(S, ray, time, h, nullptr); ph.gen = gen; ph.seg = seg; ph.kt0 = kt0; ph.shader = -1;
+  if (!ph.isHit) return;
+  const FPrim P = S.prims[h.prim]; const FXform& X = S.xforms[h.hitXform];
+  ph.shader = h.shaderOverride >= 0 ? h.shaderOverride : P.shader;
+  ph.fwd = xfPoint(X.m, h.loc); ph.nrm = norm3(xfVector(X.adj, primNormal(S, P, h.loc, h.arg0, h.arg1, h.state))); ph.rawDir = h.rawDir;
+}
+// myObjShader.findCausticRayHit: next segment off a specular surface; scales pwr. Returns false when the walk ends here.
+__device__ inline bool phSpecular(const DScene& S, const FShader& sh, const PhHit& h, double pwr[3], D3& dir, double& kt0) {
+  if (!((h.gen < S.g.numPhotonRays) && (sh.flags & SF_HAS_CAUSTIC))) return false;
+  double pm[3] = {1.0, 1.0, 1.0}; bool have = false; kt0 = 1;
+  if ((sh.KTrans > 0.0) || (sh.currPerm > 0.0)) {
+    pm[0] = sh.phtnPermClr[0]; pm[1] = sh.phtnPermClr[1]; pm[2] = sh.phtnPermClr[2];
+    Fres f = fresnel(h.rawDir, h.nrm, sh.KTrans, h.kt0);
+    if (f.oneM > DRT_EPS) dir = refractDir(f); else dir = scale3(reflDir(f.back, f.N), f.mult);
+    kt0 = sh.KTrans; have = true;
+  } else if (sh.KRefl > 0.0) {
+    pm[0] = pm[1] = pm[2] = sh.KRefl; dir = reflDir(scale3(h.rawDir, -1), h.nrm); have = true;
+  }
+  for (int i = 0; i < 3; ++i) pwr[i] = pwr[i] * pm[i];
+  return have;
+}
+
+// one thread = photon index (i0 + g / numLights) of light (g % numLights); stores go to fixed slots g*maxStore.. and are compacted afterwards
+__global__ void __launch_bounds__(128) k_photon_emit(const __grid_constant__ DScene S, long long i0, long long nThreads, int maxStore, PhotonRec* __restrict__ slots, uint32_t* __restrict__ slotCount, Counters* ctr) {
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; unsigned long long segs = 0;
+  if (g < nThreads) {
+    const int nl = S.g.numLights; PhSampler sp; sp.seed = S.g.seed; sp.photon = (uint32_t)(i0 + g / nl); sp.light = (uint32_t)(g % nl);
+    const FLight L = S.lights[sp.light]; const bool caustic = S.g.photonKind == 1;
+    const double pwrMult = (caustic ? S.g.causticPwrMult : S.g.diffusePwrMult) / S.g.numPhotonsCast;
+    double pwr[3] = {L.color[0] * pwrMult, L.color[1] * pwrMult, L.color[2] * pwrMult};
+    PhotonRec* out = slots + g * maxStore; int nStore = 0;
+    auto store = [&](const PhHit& h) { if (nStore < maxStore) { PhotonRec r; r.x = h.fwd.x; r.y = h.fwd.y; r.z = h.fwd.z; r.r = pwr[0]; r.g = pwr[1]; r.b = pwr[2]; out[nStore] = r; } ++nStore; };
+    D3 o, d; phGenRay(S, L, sp, o, d);
+    PhHit h; ++segs; phTrace(S, o, d, 0, 0, 1.0, sp, h);
+    if (caustic) {
+      if (h.isHit && (S.shaders[h.shader].flags & SF_HAS_CAUSTIC)) {
+        int lastGen = 0; bool have;
+        do {
+          const FShader sh = S.shaders[h.shader]; D3 nd; double kt0;
+          have = phSpecular(S, sh, h, pwr, nd, kt0);
+          if (have) { lastGen = h.gen + 1; ++segs; phTrace(S, h.fwd, nd, h.gen + 1, h.seg + 1, kt0, sp, h); }
+          else h.isHit = false;
+        } while (h.isHit && (S.shaders[h.shader].flags & SF_HAS_CAUSTIC) && (lastGen <= S.g.numPhotonRays));
+        if (h.isHit && !(lastGen > S.g.numPhotonRays)) store(h);
+      }
+    } else if (h.isHit) {
+      bool done = false, firstDiff = true;
+      do {
+        const FShader sh = S.shaders[h.shader];
+        if (sh.KRefl == 0) {
+          double prob = 0; const uint32_t seg = h.seg + 1; uint32_t dr = 0;
+          if (!firstDiff) { store(h); prob = urange(sp.u(seg, dr++), 0, 1.0); }
+          firstDiff = false;
+          if (prob < sh.avgDiff) {
+            double x, y, z, sq;
+            do { x = urange(sp.u(seg, dr), -1.0, 1.0); y = urange(sp.u(seg, dr + 1), -1.0, 1.0); dr += 2; sq = (x * x) + (y * y); } while ((sq >= 1.0) || (sq < DRT_EPS));
+            z = sqrt(1 - (sq));
+            D3 n = h.nrm; double nxSq = n.x * n.x, nySq = n.y * n.y, nzSq = n.z * n.z;
+            D3 tmpV = ((nxSq > nySq) && (nxSq > nzSq)) ? d3(0, 0, 1) : d3(1, 0, 0);
+            D3 p_ = cross3(n, tmpV), q_ = cross3(p_, n);
+            n = scale3(n, z); p_ = scale3(p_, x); q_ = scale3(q_, y);
+            D3 bd = d3(n.x + p_.x + q_.x, n.y + p_.y + q_.y, n.z + p_.z + q_.z);
+            pwr[0] = pwr[0] * sh.phtnDiffScl[0]; pwr[1] = pwr[1] * sh.phtnDiffScl[1]; pwr[2] = pwr[2] * sh.phtnDiffScl[2];
+            ++segs; phTrace(S, h.fwd, bd, h.gen + 1, seg, 1.0, sp, h);
+          } else done = true;
+        } else {
+          D3 nd; double kt0;
+          if (phSpecular(S, sh, h, pwr, nd, kt0)) { ++segs; phTrace(S, h.fwd, nd, h.gen + 1, h.seg + 1, kt0, sp, h); }
+          else h.isHit = false;
+        }
+      } while (h.isHit && !done && (h.gen <= S.g.numPhotonRays));
+    }
+    slotCount[g] = (uint32_t)(nStore < maxStore ? nStore : maxStore);
+  }
+  warpAdd(&ctr->pad, segs);
+}
+
+// compaction of the fixed slots into the canonical record order
+__global__ void k_photon_compact(long long nThreads, int maxStore, const PhotonRec* __restrict__ slots, const uint32_t* __restrict__ slotCount, const uint32_t* __restrict__ slotOffset, PhotonRec* __restrict__ out) {
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (g >= nThreads) return;
+  uint32_t c = slotCount[g], o = slotOffset[g];
+  for (uint32_t i = 0; i < c; ++i) out[o + i] = slots[g * maxStore + i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// grid build
+// ---------------------------------------------------------------------------------------------------------------
+struct PhGrid { double gmin[3]; double cell; uint32_t dim[3]; uint32_t nCells; };
+
+__global__ void k_photon_bounds(const PhotonRec* __restrict__ rec, long long n, double* __restrict__ blockMinMax /*[grid][6]*/) {
+  double mn[3] = {DRT_DMAX, DRT_DMAX, DRT_DMAX}, mx[3] = {-DRT_DMAX, -DRT_DMAX, -DRT_DMAX};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const PhotonRec r = rec[i]; double p[3] = {r.x, r.y, r.z};
+    for (int k = 0; k < 3; ++k) { mn[k] = fmin(mn[k], p[k]); mx[k] = fmax(mx[k], p[k]); }
+  }
+  __shared__ double sm[8][6];
+  for (int k = 0; k < 3; ++k) for (int o = 16; o > 0; o >>= 1) { mn[k] = fmin(mn[k], __shfl_down_sync(0xffffffffu, mn[k], o)); mx[k] = fmax(mx[k], __shfl_down_sync(0xffffffffu, mx[k], o)); }
+  if ((threadIdx.x & 31) == 0) for (int k = 0; k < 3; ++k) { sm[threadIdx.x >> 5][k] = mn[k]; sm[threadIdx.x >> 5][3 + k] = mx[k]; }
+  __syncthreads();
+  if (threadIdx.x < 3) { double a = sm[0][threadIdx.x], b = sm[0][3 + threadIdx.x]; for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a = fmin(a, sm[w][threadIdx.x]); b = fmax(b, sm[w][3 + threadIdx.x]); }
+    blockMinMax[blockIdx.x * 6 + threadIdx.x] = a; blockMinMax[blockIdx.x * 6 + 3 + threadIdx.x] = b; }
+}
+__device__ __forceinline__ int phCellCoord(double v, double gmin, double cell, int dim) { int c = (int)floor((v - gmin) / cell); return c < 0 ? 0 : (c >= dim ? dim - 1 : c); }
+__global__ void k_photon_cellkeys(const PhotonRec* __restrict__ rec, long long n, PhGrid G, uint32_t* __restrict__ keys, uint32_t* __restrict__ cellCount) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  const PhotonRec r = rec[i];
+  uint32_t cx = phCellCoord(r.x, G.gmin[0], G.cell, G.dim[0]), cy = phCellCoord(r.y, G.gmin[1], G.cell, G.dim[1]), cz = phCellCoord(r.z, G.gmin[2], G.cell, G.dim[2]);
+  uint32_t key = (cz * G.dim[1] + cy) * G.dim[0] + cx; keys[i] = key; atomicAdd(&cellCount[key], 1u);
+}
+// sorted order -> the two 32-byte-per-photon arrays the gather reads with 128-bit loads
+__global__ void k_photon_reorder(const PhotonRec* __restrict__ rec, const uint32_t* __restrict__ order, long long n, double4* __restrict__ pos, double4* __restrict__ pwr) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  const PhotonRec r = rec[order[i]]; pos[i] = make_double4(r.x, r.y, r.z, 0.0); pwr[i] = make_double4(r.r, r.g, r.b, 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// gather
+// ---------------------------------------------------------------------------------------------------------------
+#define DRT_PH_BINS 256
+#define DRT_PH_LIST 128
+struct PhWarpShared { uint32_t hist[DRT_PH_BINS]; double listD2[DRT_PH_LIST]; uint32_t listIdx[DRT_PH_LIST]; uint32_t listN; uint32_t pad[3]; };
+
+// Sum of the powers of the k nearest photons with d^2 < r^2 around p, and the largest of their d^2 -- computed by one warp.
+// Selection = radix select on a 32-bit quantisation of d^2 (monotone in d^2), 8 bits per level over the candidate rows of the grid,
+// finished exactly (double d^2, index tie-break) on the short list of the boundary bin.
+__device__ inline void phWarpGather(const DScene& S, D3 p, PhWarpShared& sh, double sum[3], double& dmax2, unsigned long long* visited) {
+  const unsigned lane = threadIdx.x & 31; const double r2 = S.g.phMaxDist2; const int K = S.g.kNhood;
+  sum[0] = sum[1] = sum[2] = 0; dmax2 = 0;
+  if (S.numPhotons == 0 || K <= 0) return;
+  const double rr = sqrt(r2) * 1.0000001, cell = S.cellSize;
+  int lo[3], hi[3]; const double pp[3] = {p.x, p.y, p.z}; bool empty = false;
+  for (int k = 0; k < 3; ++k) {
+    double a = floor((pp[k] - rr - S.gridMin[k]) / cell), b = floor((pp[k] + rr - S.gridMin[k]) / cell); const int dim = (int)S.gridDim[k];
+    if (!(b >= 0) || !(a <= dim - 1)) empty = true;
+    lo[k] = a < 0 ? 0 : (int)a; hi[k] = b > dim - 1 ? dim - 1 : (int)b;
+  }
+  if (empty) return;
+  const double qscale = 4294967295.0 / r2;          // quantised key: monotone non-decreasing in d^2, < 2^32 for d^2 < r^2
+  const double4* __restrict__ P = reinterpret_cast<const double4*>(S.phPos); const double4* __restrict__ W = reinterpret_cast<const double4*>(S.phPwr);
+  // visit every candidate of the 3x3 (or so) rows of cells; F(j, d2, q) is called for candidates with d2 < r2
+  auto forEach = [&](auto&& F) {
+    for (int cz = lo[2]; cz <= hi[2]; ++cz) for (int cy = lo[1]; cy <= hi[1]; ++cy) {
+      const uint32_t row = ((uint32_t)cz * S.gridDim[1] + (uint32_t)cy) * S.gridDim[0];
+      const uint32_t a = S.cellStart[row + lo[0]], b = S.cellStart[row + hi[0] + 1];
+      for (uint32_t j0 = a; j0 < b; j0 += 32) {
+        const uint32_t j = j0 + lane; bool ok = j < b; double d2 = 0;
+        if (ok) { const double4 q = P[j]; const double dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z; d2 = dx * dx + dy * dy + dz * dz; ok = d2 < r2; }
+        F(j, d2, ok ? (uint32_t)(d2 * qscale) : 0u, ok);
+      }
+    }
+  };
+  // level loop: keys with (q >> shift) < prefix are already known to be inside; those == prefix are undecided
+  uint32_t prefix = 0; int shift = 32; int need = K; bool takeAllUndecided = false, haveList = false;
+  while (true) {
+    const int nshift = shift - 8;
+    for (int i = lane; i < DRT_PH_BINS; i += 32) sh.hist[i] = 0;
+    __syncwarp();
+    unsigned m = 0, vis = 0;
+    forEach([&](uint32_t, double, uint32_t q, bool ok) {
+      const bool und = ok && (shift == 32 || (q >> shift) == prefix);
+      if (und) atomicAdd(&sh.hist[(q >> nshift) & 255u], 1u);
+      m += __popc(__ballot_sync(0xffffffffu, und)); vis += 32;
+    });
+    if (visited && shift == 32 && lane == 0) *visited += vis;
+    __syncwarp();
+    if ((int)m <= need) { takeAllUndecided = true; break; }                 // fewer undecided candidates than still needed: all of them are in
+    // find the bin where the running count reaches `need`
+    uint32_t loc[8], s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { loc[i] = sh.hist[lane * 8 + i]; s += loc[i]; }
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
+    const unsigned reach = __ballot_sync(0xffffffffu, incl >= (uint32_t)need); const int L = __ffs(reach) - 1;
+    uint32_t binSel = 0, before = 0, inBin = 0;
+    if ((int)lane == L) { uint32_t c = incl - s; for (int i = 0; i < 8; ++i) { if (c + loc[i] >= (uint32_t)need) { binSel = lane * 8 + i; before = c; inBin = loc[i]; break; } c += loc[i]; } }
+    binSel = __shfl_sync(0xffffffffu, binSel, L); before = __shfl_sync(0xffffffffu, before, L); inBin = __shfl_sync(0xffffffffu, inBin, L);
+    need -= (int)before; prefix = (shift == 32) ? binSel : ((prefix << 8) | binSel); shift = nshift;
+    if (inBin <= DRT_PH_LIST) { haveList = true; break; }
+    if (shift == 0) break;                                                    // > DRT_PH_LIST photons with identical 32-bit distance keys: take by index order below
+  }
+  // final pass: accumulate everything decided-in; collect the boundary bin
+  if (lane == 0) sh.listN = 0;
+  __syncwarp();
+  double s0 = 0, s1 = 0, s2 = 0, mx = 0; int tieTaken = 0;
+  forEach([&](uint32_t j, double d2, uint32_t q, bool ok) {
+    bool in = false, bnd = false;
+    if (ok) {
+      if (takeAllUndecided) in = (shift == 32) || ((q >> shift) <= prefix);
+      else { const uint32_t hb = q >> shift; in = hb < prefix; bnd = hb == prefix; }
+    }
+    const unsigned bm = __ballot_sync(0xffffffffu, bnd);
+    if (haveList) {
+      if (bnd) { const uint32_t at = sh.listN + __popc(bm & ((1u << lane) - 1u)); if (at < DRT_PH_LIST) { sh.listD2[at] = d2; sh.listIdx[at] = j; } }
+      __syncwarp();
+      if (lane == 0) sh.listN += __popc(bm);
+      __syncwarp();
+    } else if (bm) {          // degenerate ties (> DRT_PH_LIST equal 32-bit keys): first `need` in index order
+      if (bnd) in = (tieTaken + __popc(bm & ((1u << lane) - 1u))) < need;
+      tieTaken += __popc(bm);
+    }
+    if (in) { const double4 w = W[j]; s0 += w.x; s1 += w.y; s2 += w.z; mx = fmax(mx, d2); }
+  });
+  if (haveList) {   // exact selection of the `need` smallest (d2, index) of the boundary list
+    __syncwarp();
+    const int n = (int)min(sh.listN, (uint32_t)DRT_PH_LIST);
+    for (int i = lane; i < n; i += 32) {
+      const double di = sh.listD2[i]; const uint32_t ji = sh.listIdx[i]; int rank = 0;
+      for (int t = 0; t < n; ++t) { const double dt = sh.listD2[t]; rank += (dt < di || (dt == di && sh.listIdx[t] < ji)) ? 1 : 0; }
+      if (rank < need) { const double4 w = W[ji]; s0 += w.x; s1 += w.y; s2 += w.z; mx = fmax(mx, di); }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  sum[0] = s0; sum[1] = s1; sum[2] = s2; dmax2 = mx;
+}
+
+// One warp serves the 32 surface records it owns, one query at a time. Runs between k_shade (local = ambient) and k_light
+// (local += direct), which is the reference's accumulation order (myObjShader.java:413-425).
+__global__ void __launch_bounds__(128) k_photon_gather(const __grid_constant__ DScene S, long long n, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, Counters* ctr) {
+  __shared__ PhWarpShared shw[4];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; const unsigned lane = threadIdx.x & 31;
+  bool needs = false; D3 loc = d3(0, 0, 0); int shIdx = -1;
+  if (i < n) { const SurfRec s = surf[i]; if (s.valid) { shIdx = s.shader; const FShader& sh = S.shaders[shIdx];
+      needs = !(sh.flags & SF_SIMPLE) && (sh.KRefl == 0.0) && (sh.flags & SF_USE_PHOTON); loc = d3(s.loc[0], s.loc[1], s.loc[2]); } }
+  unsigned mask = __ballot_sync(0xffffffffu, needs);
+  while (mask) {
+    const int src = __ffs(mask) - 1; mask &= mask - 1;
+    D3 p = d3(__shfl_sync(0xffffffffu, loc.x, src), __shfl_sync(0xffffffffu, loc.y, src), __shfl_sync(0xffffffffu, loc.z, src));
+    double sum[3], dmax2; phWarpGather(S, p, shw[threadIdx.x >> 5], sum, dmax2, nullptr);
+    if ((int)lane == src && dmax2 > 0) {
+      const double area = DRT_PI_F * dmax2; const D3 irr = d3(sum[0] / area, sum[1] / area, sum[2] / area); const FShader& sh = S.shaders[shIdx];
+      double* l = nodes[i].local;
+      if (sh.flags & SF_IS_CAUSTIC_PHTN) { l[0] = l[0] + irr.x; l[1] = l[1] + irr.y; l[2] = l[2] + irr.z; }
+      else { l[0] = l[0] + sh.diff[0] * irr.x; l[1] = l[1] + sh.diff[1] * irr.y; l[2] = l[2] + sh.diff[2] * irr.z; }
+    }
+    __syncwarp();
+  }
+  (void)ctr;
+}
+
+// parity probe: irradiance estimate at explicit points (one warp per point): out = {sum r,g,b, dmax2, count visited}
+__global__ void __launch_bounds__(128) k_photon_probe(const __grid_constant__ DScene S, long long n, const double* __restrict__ pts, double* __restrict__ out) {
+  __shared__ PhWarpShared shw[4];
+  const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; if (q >= n) return;
+  double sum[3], dmax2; unsigned long long vis = 0; phWarpGather(S, d3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]), shw[threadIdx.x >> 5], sum, dmax2, &vis);
+  if ((threadIdx.x & 31) == 0) { out[5 * q] = sum[0]; out[5 * q + 1] = sum[1]; out[5 * q + 2] = sum[2]; out[5 * q + 3] = dmax2; out[5 * q + 4] = (double)vis; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+struct PhotonMap {
+  bool built = false, emitted = false; unsigned long long count = 0, segments = 0;
+  PhotonRec* rec = nullptr; size_t recCap = 0;                  // canonical-order records (emission output / grid input)
+  double4 *pos = nullptr, *pwr = nullptr; uint32_t* cellStart = nullptr; size_t sortedCap = 0, cellCap = 0;
+  PhGrid grid{}; float msEmit = 0, msBuild = 0;
+
+  void reset() { built = false; emitted = false; count = 0; segments = 0; }
+  void release() { cudaFree(rec); cudaFree(pos); cudaFree(pwr); cudaFree(cellStart); rec = nullptr; pos = pwr = nullptr; cellStart = nullptr; recCap = sortedCap = cellCap = 0; reset(); }
+  void ensureRec(size_t n, cudaStream_t st) {
+    if (n <= recCap) return;
+    size_t nc = n + n / 2 + 4096; PhotonRec* q = nullptr; CK(cudaMalloc(&q, nc * sizeof(PhotonRec)));
+    if (rec && count) CK(cudaMemcpyAsync(q, rec, count * sizeof(PhotonRec), cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st)); cudaFree(rec); rec = q; recCap = nc;
+  }
+
+  // photons [i0, i1) of every light -> appended to `rec` in canonical order. Chunked so the slot buffer stays bounded.
+  void emitRange(const DScene& ds, long long i0, long long i1, Counters* ctr, Counters* ctrHost, cudaStream_t st) {
+    built = false; emitted = true; count = 0; segments = 0;
+    const int nl = ds.g.numLights; if (nl <= 0 || i1 <= i0 || ds.g.photonKind == 0) return;
+    const int maxStore = ds.g.photonKind == 1 ? 1 : (ds.g.numPhotonRays + 1);
+    const long long chunkPhotons = std::max<long long>(1, (1ll << 21) / nl);
+    const long long maxThreads = std::min(chunkPhotons, i1 - i0) * nl;
+    PhotonRec* slots = nullptr; uint32_t *cnt = nullptr, *off = nullptr, *scratch = nullptr;
+    CK(cudaMalloc(&slots, (size_t)maxThreads * maxStore * sizeof(PhotonRec))); CK(cudaMalloc(&cnt, (size_t)(maxThreads + 1) * 4)); CK(cudaMalloc(&off, (size_t)(maxThreads + 1) * 4));
+    CK(cudaMalloc(&scratch, (size_t)scanScratchWords(maxThreads + 1) * 4));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventRecord(e0, st));
+    CK(cudaMemsetAsync(&ctr->pad, 0, sizeof(unsigned long long), st));
+    try {
+      for (long long c0 = i0; c0 < i1; c0 += chunkPhotons) {
+        const long long np = std::min(chunkPhotons, i1 - c0), nt = np * nl;
+        CK(cudaMemsetAsync(cnt + nt, 0, 4, st));
+        k_photon_emit<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(ds, c0, nt, maxStore, slots, cnt, ctr);
+        scanExclusiveU32(cnt, off, nt + 1, scratch, st);
+        uint32_t total = 0; CK(cudaMemcpyAsync(&total, off + nt, 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        ensureRec(count + total, st);
+        if (total) k_photon_compact<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(nt, maxStore, slots, cnt, off, rec + count);
+        count += total;
+      }
+      CK(cudaMemcpyAsync(ctrHost, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+      CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+      segments = ctrHost->pad; CK(cudaEventElapsedTime(&msEmit, e0, e1));
+    } catch (...) { cudaFree(slots); cudaFree(cnt); cudaFree(off); cudaFree(scratch); cudaEventDestroy(e0); cudaEventDestroy(e1); throw; }
+    cudaFree(slots); cudaFree(cnt); cudaFree(off); cudaFree(scratch); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+  // replace the record store with `n` records that already live on the device (multi-GPU: the all-gathered set)
+  void setRecords(const PhotonRec* srcDev, unsigned long long n, cudaStream_t st) {
+    built = false; emitted = true; count = 0; ensureRec((size_t)n, st);
+    if (n) CK(cudaMemcpyAsync(rec, srcDev, n * sizeof(PhotonRec), cudaMemcpyDeviceToDevice, st));
+    count = n; CK(cudaStreamSynchronize(st));
+  }
+
+  void buildGrid(DScene& ds, cudaStream_t st) {
+    ds.numPhotons = 0; ds.phPos = nullptr; ds.phPwr = nullptr; ds.cellStart = nullptr; ds.cellEnd = nullptr; built = true; msBuild = 0;
+    if (count == 0) return;
+    if (count >= 0xFFFFFFF0ull) throw std::runtime_error("photon map larger than 2^32 records");
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventRecord(e0, st));
+    const long long n = (long long)count;
+    // bounds
+    const int nbB = 592; double* bmm = nullptr; CK(cudaMalloc(&bmm, nbB * 6 * sizeof(double)));
+    k_photon_bounds<<<nbB, 256, 0, st>>>(rec, n, bmm);
+    std::vector<double> hb(nbB * 6); CK(cudaMemcpyAsync(hb.data(), bmm, hb.size() * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); cudaFree(bmm);
+    double mn[3] = {DRT_DMAX, DRT_DMAX, DRT_DMAX}, mx[3] = {-DRT_DMAX, -DRT_DMAX, -DRT_DMAX};
+    for (int b = 0; b < nbB; ++b) for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], hb[b * 6 + k]); mx[k] = std::max(mx[k], hb[b * 6 + 3 + k]); }
+    double cell = std::sqrt(ds.g.phMaxDist2); if (!(cell > 0)) cell = 1e-3;
+    PhGrid G;
+    while (true) {
+      double cells = 1; for (int k = 0; k < 3; ++k) { double d = std::floor((mx[k] - mn[k]) / cell) + 1; if (d < 1) d = 1; G.dim[k] = (uint32_t)std::min(d, 4.0e9); cells *= d; }
+      if (cells <= (double)(1u << 26)) break;
+      cell *= 2;
+    }
+    G.cell = cell; for (int k = 0; k < 3; ++k) G.gmin[k] = mn[k]; G.nCells = G.dim[0] * G.dim[1] * G.dim[2]; grid = G;
+    // keys + per-cell counts, cellStart = exclusive scan (nCells + 1 entries: cellStart[nCells] = n)
+    if ((size_t)G.nCells + 1 > cellCap) { cudaFree(cellStart); cellCap = (size_t)G.nCells + 1; CK(cudaMalloc(&cellStart, cellCap * 4)); }
+    if ((size_t)n > sortedCap) { cudaFree(pos); cudaFree(pwr); sortedCap = (size_t)n + (size_t)n / 8 + 1024; CK(cudaMalloc(&pos, sortedCap * sizeof(double4))); CK(cudaMalloc(&pwr, sortedCap * sizeof(double4))); }
+    uint32_t *keys[2], *vals[2], *hist, *scratch; const long long nb = radixBlocks(n);
+    for (int k = 0; k < 2; ++k) { CK(cudaMalloc(&keys[k], (size_t)n * 4)); CK(cudaMalloc(&vals[k], (size_t)n * 4)); }
+    const long long scanWords = std::max(scanScratchWords(256 * nb), scanScratchWords((long long)G.nCells + 1));
+    CK(cudaMalloc(&hist, (size_t)256 * nb * 4)); CK(cudaMalloc(&scratch, (size_t)scanWords * 4));
+    CK(cudaMemsetAsync(cellStart, 0, ((size_t)G.nCells + 1) * 4, st));
+    k_photon_cellkeys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, n, G, keys[0], cellStart);
+    scanExclusiveU32(cellStart, cellStart, (long long)G.nCells + 1, scratch, st);
+    int bits = 1; while ((1ull << bits) < (unsigned long long)G.nCells) ++bits;
+    const int cur = radixSortPairs(keys, vals, n, bits, true, hist, scratch, st);
+    k_photon_reorder<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, vals[cur], n, pos, pwr);
+    CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError()); CK(cudaEventElapsedTime(&msBuild, e0, e1));
+    for (int k = 0; k < 2; ++k) { cudaFree(keys[k]); cudaFree(vals[k]); } cudaFree(hist); cudaFree(scratch); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ds.numPhotons = (uint32_t)n; ds.phPos = reinterpret_cast<const double*>(pos); ds.phPwr = reinterpret_cast<const double*>(pwr); ds.cellStart = cellStart; ds.cellEnd = nullptr;
+    for (int k = 0; k < 3; ++k) { ds.gridDim[k] = G.dim[k]; ds.gridMin[k] = G.gmin[k]; } ds.cellSize = G.cell;
+  }
+
+  void emitAndBuild(DScene& ds, Counters* ctr, Counters* ctrHost, cudaStream_t st) { emitRange(ds, 0, ds.g.numPhotonsCast, ctr, ctrHost, st); buildGrid(ds, st); }
+
+  long long download(double* out6, long long cap, cudaStream_t st) {
+    long long n = std::min<long long>((long long)count, cap); if (n <= 0 || !out6) return (long long)count;
+    CK(cudaMemcpyAsync(out6, rec, (size_t)n * sizeof(PhotonRec), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); return n;
+  }
+};
+
 }  // namespace drt

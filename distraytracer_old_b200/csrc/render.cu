@@ -126,9 +126,6 @@ __device__ inline D3 skyColor(const DScene& S, D3 o, D3 d) {
   return colorOfArgb(S.texels[im.offset + idx]);
 }
 
-// photon radiance estimate, defined in photon.cuh (hash-grid kNN gather)
-__device__ D3 photonIrradiance(const DScene& S, D3 p);
-
 // Surface pass. One thread per ray of the level; children go to the next level's queue.
 __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene S, long long n, const RayRec* __restrict__ rays, const Hit* __restrict__ hits,
                                                SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, RayRec* __restrict__ nextRays, NodeRec* __restrict__ nextNodes,
@@ -151,12 +148,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene S,
         D3 fwd = xfPoint(X.m, h.loc);
         D3 nrm = norm3(xfVector(X.adj, primNormal(S, P, h.loc, h.arg0, h.arg1, h.state)));
         local = d3(sh.amb[0], sh.amb[1], sh.amb[2]);
-        const bool simple = (sh.flags & SF_SIMPLE) != 0;
-        if (!simple && (sh.KRefl == 0.0) && (sh.flags & SF_USE_PHOTON) && S.numPhotons > 0) {
-          D3 irr = photonIrradiance(S, fwd);
-          if (sh.flags & SF_IS_CAUSTIC_PHTN) local = add3(local, irr);
-          else local = d3(local.x + sh.diff[0] * irr.x, local.y + sh.diff[1] * irr.y, local.z + sh.diff[2] * irr.z);
-        }
+        const bool simple = (sh.flags & SF_SIMPLE) != 0;       // (the photon term is added by k_photon_gather, which runs next)
         double time = rayTime(S, r.stream, r.ka, r.kb, r.kc, DIM_TIME);
         D3 tex = evalTexture(S, sh, P, h.loc, fwd, h.state, time);
         s.valid = 1; s.shader = shIdx;
@@ -391,11 +383,11 @@ void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank,
   pm.chunkPix = (pm.world == 1) ? (pm.totalPix > 0 ? pm.totalPix : 1) : (long long)chunkRows * g_.cols;
   if (pm.world > 1) { long long nChunks = (g_.rows + chunkRows - 1) / chunkRows, mine = (nChunks - rank + world - 1) / world; pix0 = 0; pix1 = mine * pm.chunkPix; }
   if (!I.ds.prims) throw std::runtime_error("render called before a scene was uploaded");
-  if (g_.photonKind != 0 && !I.photons.built) { I.photons.emitAndBuild(I.ds, st, stats); }
+  if (g_.photonKind != 0 && !I.photons.built) { if (!I.photons.emitted) I.photons.emitRange(I.ds, 0, g_.numPhotonsCast, I.ctr, I.ctrHost, st); I.photons.buildGrid(I.ds, st); }
   const int spp = g_.spp < 1 ? 1 : g_.spp;
   long long pixPerBatch = batchRays_ / spp; if (pixPerBatch < 1) pixPerBatch = 1;
   RenderStats rs; std::memset(&rs, 0, sizeof(rs)); if (stats) { rs.photonSeg = stats->photonSeg; rs.photonsStored = stats->photonsStored; }
-  rs.photonsStored = I.photons.count;
+  rs.photonsStored = I.photons.count; rs.photonSeg = I.photons.segments;
   float msT = 0, msS = 0, msL = 0;
   CK(cudaEventRecord(I.ev[0], st));
   for (long long b0 = pix0; b0 < pix1; b0 += pixPerBatch) {
@@ -414,6 +406,7 @@ void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank,
       else k_trace<false><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.rays[cur].p, hitBuf, I.ctr);
       CK(cudaEventRecord(I.ev[2], st));
       k_shade<<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.rays[cur].p, hitBuf, I.surf.p, I.nodes.p + off, I.rays[cur ^ 1].p, I.nodes.p + off + n, I.ctr, nextCap);
+      if (I.ds.numPhotons > 0) { k_photon_gather<<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off, I.ctr); ++rs.kernelLaunches; }
       CK(cudaEventRecord(I.ev[3], st));
       if (counters_ || (traceMode_ & 256)) k_light<true><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off, I.ctr);
       else k_light<false><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off, I.ctr);
@@ -463,8 +456,37 @@ void Renderer::renderToHost(int32_t* argbHost, int32_t* hitPrimHost, int32_t* hi
 double hostPhiloxU01(uint64_t seed, uint32_t stream, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return philoxU01(seed, stream, a, b, c, d); }
 void Renderer::emitPhotons(RenderStats* stats) {
   CK(cudaSetDevice(device_)); Impl& I = *impl_;
-  if (g_.photonKind != 0 && !I.photons.built) I.photons.emitAndBuild(I.ds, (cudaStream_t)stream_, stats);
-  if (stats) stats->photonsStored = I.photons.count;
+  if (g_.photonKind != 0 && !I.photons.built) I.photons.emitAndBuild(I.ds, I.ctr, I.ctrHost, (cudaStream_t)stream_);
+  if (stats) { stats->photonsStored = I.photons.count; stats->photonSeg = I.photons.segments; stats->msTrace = I.photons.msEmit; stats->msOther = I.photons.msBuild; stats->msTotal = I.photons.msEmit + I.photons.msBuild; }
+}
+// multi-GPU split: emit photon indices [i0, i1) of every light (no grid build); export / import the canonical-order records on the device
+void Renderer::emitPhotonsRange(long long i0, long long i1, RenderStats* stats) {
+  CK(cudaSetDevice(device_)); Impl& I = *impl_;
+  if (g_.photonKind == 0) { I.photons.reset(); return; }
+  if (i0 < 0 || i1 > g_.numPhotonsCast || i0 > i1) throw std::runtime_error("photon index range outside [0, photons cast]");
+  I.photons.emitRange(I.ds, i0, i1, I.ctr, I.ctrHost, (cudaStream_t)stream_);
+  if (stats) { stats->photonsStored = I.photons.count; stats->photonSeg = I.photons.segments; stats->msTrace = I.photons.msEmit; stats->msTotal = I.photons.msEmit; }
+}
+long long Renderer::exportPhotonsDevice(double* dst6Dev, long long cap) {
+  CK(cudaSetDevice(device_)); Impl& I = *impl_; cudaStream_t st = (cudaStream_t)stream_;
+  long long n = std::min<long long>((long long)I.photons.count, cap);
+  if (n > 0 && dst6Dev) { CK(cudaMemcpyAsync(dst6Dev, I.photons.rec, (size_t)n * sizeof(PhotonRec), cudaMemcpyDeviceToDevice, st)); CK(cudaStreamSynchronize(st)); }
+  return (long long)I.photons.count;
+}
+void Renderer::buildPhotonsFromDevice(const double* src6Dev, long long n, RenderStats* stats) {
+  CK(cudaSetDevice(device_)); Impl& I = *impl_; cudaStream_t st = (cudaStream_t)stream_;
+  if (n < 0 || (n > 0 && !src6Dev)) throw std::runtime_error("bad photon record buffer");
+  I.photons.setRecords(reinterpret_cast<const PhotonRec*>(src6Dev), (unsigned long long)n, st); I.photons.buildGrid(I.ds, st);
+  if (stats) { stats->photonsStored = I.photons.count; stats->msOther = I.photons.msBuild; stats->msTotal = I.photons.msBuild; }
+}
+void Renderer::probePhotons(long long n, const double* ptsHost, double* out5Host) {
+  CK(cudaSetDevice(device_)); Impl& I = *impl_; cudaStream_t st = (cudaStream_t)stream_;
+  if (g_.photonKind != 0 && !I.photons.built) I.photons.emitAndBuild(I.ds, I.ctr, I.ctrHost, st);
+  double *a, *b; CK(cudaMalloc(&a, n * 24)); CK(cudaMalloc(&b, n * 40));
+  CK(cudaMemcpyAsync(a, ptsHost, n * 24, cudaMemcpyHostToDevice, st)); CK(cudaMemsetAsync(b, 0, n * 40, st));
+  if (I.ds.numPhotons > 0) k_photon_probe<<<gridFor(n * 32, 128), 128, 0, st>>>(I.ds, n, a, b);
+  CK(cudaMemcpyAsync(out5Host, b, n * 40, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+  cudaFree(a); cudaFree(b);
 }
 long long Renderer::getPhotons(double* out6Host, long long cap) { CK(cudaSetDevice(device_)); return impl_->photons.download(out6Host, cap, (cudaStream_t)stream_); }
 

@@ -35,6 +35,10 @@ class Renderer {
   void evalTexture(int shaderIdx, long long n, const double* hitLocHost, const double* fwdLocHost, double* outHost);
   void emitPhotons(RenderStats* stats);               // builds the photon map if the scene asks for one
   long long getPhotons(double* out6Host, long long cap);
+  void emitPhotonsRange(long long i0, long long i1, RenderStats* stats);          // photon indices [i0,i1) of every light, no grid build
+  long long exportPhotonsDevice(double* dst6Dev, long long cap);                  // canonical-order records -> caller's device buffer; returns count
+  void buildPhotonsFromDevice(const double* src6Dev, long long n, RenderStats* stats);   // replace the record set (e.g. all-gathered) and build the grid
+  void probePhotons(long long n, const double* ptsHost, double* out5Host);       // per point: sum r,g,b of the k nearest, d^2 of the farthest, candidates visited
   int cols() const { return g_.cols; }
   int rows() const { return g_.rows; }
   int spp() const { return g_.spp; }

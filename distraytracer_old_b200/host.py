@@ -79,6 +79,10 @@ def load_library():
         "drt_obj_ctm": (C.c_int, [vp, i32, vp]),
         "drt_sample_u01": (dbl, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
         "drt_get_photons": (i64, [vp, vp, i64]),
+        "drt_emit_photons_range": (C.c_int, [vp, i64, i64, C.POINTER(Stats)]),
+        "drt_photons_export_device": (i64, [vp, vp, i64]),
+        "drt_photons_build_device": (C.c_int, [vp, vp, i64, C.POINTER(Stats)]),
+        "drt_photon_probe": (C.c_int, [vp, i64, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -91,7 +95,8 @@ def load_library():
 EXPORTS = ["drt_create", "drt_destroy", "drt_last_error", "drt_set_image_loader", "drt_set_texture_dir", "drt_scene_reset",
            "drt_scene_command", "drt_scene_load_cli", "drt_scene_override", "drt_scene_finalize", "drt_scene_reupload",
            "drt_scene_info", "drt_emit_photons", "drt_render", "drt_render_aov", "drt_render_device", "drt_render_device_chunks", "drt_save_png",
-           "drt_trace_rays", "drt_eval_texture", "drt_dump_bvh", "drt_obj_ctm", "drt_sample_u01", "drt_get_photons"]
+           "drt_trace_rays", "drt_eval_texture", "drt_dump_bvh", "drt_obj_ctm", "drt_sample_u01", "drt_get_photons",
+           "drt_emit_photons_range", "drt_photons_export_device", "drt_photons_build_device", "drt_photon_probe"]
 
 
 def decode_image_argb(path):
@@ -228,6 +233,29 @@ class Scene:
         out = np.zeros((max(n, 1), 6), dtype=np.float64)
         m = self.L.drt_get_photons(self.ctx.h, out.ctypes.data, min(n, cap))
         return out[:max(m, 0)]
+
+    def emit_photons_range(self, i0, i1):
+        st = Stats()
+        self.ctx._ck(self.L.drt_emit_photons_range(self.ctx.h, i0, i1, C.byref(st)))
+        return st
+
+    def photons_export_device(self, dev_ptr, cap):
+        n = self.L.drt_photons_export_device(self.ctx.h, dev_ptr, cap)
+        if n < 0:
+            self.ctx._ck(int(n))
+        return int(n)
+
+    def photons_build_device(self, dev_ptr, n):
+        st = Stats()
+        self.ctx._ck(self.L.drt_photons_build_device(self.ctx.h, dev_ptr, n, C.byref(st)))
+        return st
+
+    def photon_probe(self, pts):
+        """kNN radiance gather at world points: rows of {sum r, sum g, sum b, d2 of the farthest, candidates visited}."""
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        out = np.zeros((pts.shape[0], 5), dtype=np.float64)
+        self.ctx._ck(self.L.drt_photon_probe(self.ctx.h, pts.shape[0], pts.ctypes.data, out.ctypes.data))
+        return out
 
     def save(self, path, argb):
         a = np.ascontiguousarray(argb, dtype=np.int32)

@@ -65,6 +65,12 @@ int drt_scene_info(drt_ctx* ctx, int32_t* out16);                /* cols, rows, 
 
 /* ---- rendering: replaces myScene.initRender + draw; argb layout == PImage.pixels ---- */
 int drt_emit_photons(drt_ctx* ctx, drt_stats* stats);            /* myScene.sendCausticPhotons / sendDiffusePhotons (:952-1091) */
+/* multi-GPU photon pass (the reference emits serially, myScene.java:961,1009): rank r emits photon indices [i0,i1) of every light into
+ * canonical-order records {x,y,z,r,g,b} (6 doubles) on its device, the host all-gathers the records (NCCL) and every rank builds the grid
+ * from the full set.  Record order -- hence every later floating-point sum -- is independent of how the index range was split. */
+int drt_emit_photons_range(drt_ctx* ctx, int64_t i0, int64_t i1, drt_stats* stats);
+int64_t drt_photons_export_device(drt_ctx* ctx, double* dst6_dev, int64_t cap);    /* copies min(count,cap) records to a DEVICE buffer; returns count */
+int drt_photons_build_device(drt_ctx* ctx, const double* src6_dev, int64_t n, drt_stats* stats);  /* n records in a DEVICE buffer -> photon grid */
 int drt_render(drt_ctx* ctx, int32_t* argb_out, drt_stats* stats);                 /* host buffer, cols*rows */
 int drt_render_aov(drt_ctx* ctx, int32_t* argb_out, int32_t* hit_prim, int32_t* hit_inst, double* rgb, double* t, drt_stats* stats); /* any may be NULL */
 /* device-resident variant for multi-GPU hosts: render pixels [pix0,pix1) into caller-owned DEVICE buffers of cols*rows ints */
@@ -81,6 +87,8 @@ int64_t drt_dump_bvh(drt_ctx* ctx, int32_t top_index, int32_t* out, int64_t cap,
 int drt_obj_ctm(drt_ctx* ctx, int32_t top_index, double* out16);
 double drt_sample_u01(uint64_t seed, uint32_t stream, uint32_t a, uint32_t b, uint32_t c, uint32_t d);
 int64_t drt_get_photons(drt_ctx* ctx, double* out6, int64_t cap);   /* x,y,z,r,g,b per stored photon */
+/* kNN radiance gather at explicit world points (myKD_Tree.find_near + getIrradianceFromPhtnTree): out5 = {sum r, sum g, sum b, d^2 of the farthest, candidates visited} */
+int drt_photon_probe(drt_ctx* ctx, int64_t n, const double* pts3, double* out5);
 
 #ifdef __cplusplus
 }

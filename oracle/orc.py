@@ -45,6 +45,8 @@ def lib():
         L.orc_emit_photons.argtypes = [C.c_void_p]
         L.orc_get_photons.restype = C.c_longlong
         L.orc_get_photons.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+        L.orc_photon_probe.restype = C.c_longlong
+        L.orc_photon_probe.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
         L.orc_render.restype = C.c_double
         L.orc_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
         L.orc_trace_rays.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -89,6 +91,13 @@ class OracleScene:
         out = np.zeros((max(n, 1), 6), dtype=np.float64)
         m = lib().orc_get_photons(self.h, out.ctypes.data, n)
         return out[:m]
+
+    def photon_probe(self, pts):
+        """find_near at world points: rows of {sum r, sum g, sum b, d2 of the farthest of the k}."""
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        out = np.zeros((pts.shape[0], 4), dtype=np.float64)
+        lib().orc_photon_probe(self.h, pts.shape[0], pts.ctypes.data, out.ctypes.data)
+        return out
 
     def render(self, rect=None, threads=1, want=("argb", "hit_prim", "hit_inst", "rgb", "t")):
         x0, y0, x1, y1 = rect if rect else (0, 0, self.cols, self.rows)

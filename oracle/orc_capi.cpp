@@ -58,6 +58,19 @@ long long orc_get_photons(void* hv, double* out, long long cap) {
   return n;
 }
 
+// myKD_Tree.find_near + getIrradianceFromPhtnTree at explicit world points: out4 = {sum r, sum g, sum b, d^2 of the farthest neighbour}
+long long orc_photon_probe(void* hv, long long n, const double* pts, double* out4) {
+  Scene* s = ((OrcHandle*)hv)->get(0); s->initRender(); if (!s->photonTree) return 0;
+  std::vector<KDTree::Near> hood;
+  for (long long i = 0; i < n; ++i) {
+    s->photonTree->find_near(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], hood);
+    double* o = out4 + 4 * i; o[0] = o[1] = o[2] = o[3] = 0;
+    if (hood.empty()) continue;
+    o[3] = hood[0].d2; for (auto& nb : hood) { o[0] += nb.p->pwr[0]; o[1] += nb.p->pwr[1]; o[2] += nb.p->pwr[2]; }
+  }
+  return n;
+}
+
 // Render the pixel rectangle [x0,x1) x [y0,y1). Output arrays are (y1-y0)*(x1-x0), row-major; any may be NULL.
 // stats: 10 x uint64 {primary, shadow, reflect, refract, photonSeg, boxTests, primTests, boxTestsPrimary, primTestsPrimary, photonsStored}
 // returns wall seconds of the pixel loop (photon emission excluded; it is reported by orc_emit_photons' caller)
