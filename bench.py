@@ -188,9 +188,13 @@ def main():
             scene.reupload(); scene.draw_into(host.data_ptr())
         barrier(); t0 = time.perf_counter(); tot_r = 0
         for _ in range(args.steps):
+            ta = time.perf_counter()
             scene.reupload()                        # H2D of the flattened scene
+            tb = time.perf_counter()
             st = scene.draw_into(host.data_ptr())   # kernels + D2H of the ARGB frame into pinned host memory
             tot_r += st.rays_total
+            if os.environ.get("DRT_BENCH_DEBUG"):
+                print("e2e step: reupload %.1f ms, draw_into %.1f ms (gpu %.1f)" % ((tb - ta) * 1e3, (time.perf_counter() - tb) * 1e3, st.ms_total), file=sys.stderr, flush=True)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
         e2e_val = tot_r / dt / 1e6
         if dist is not None:     # every rank rendered a full frame here; report the slowest rank's single-GPU figure
