@@ -194,6 +194,127 @@ __device__ __noinline__ bool primTest(const DScene& S, int primIdx, const Ray& r
   return false;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// fast BVHs: packed triangles, both child boxes per node, near-first ordered descent with global pruning
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldTri(const FTri* __restrict__ p, double (&w)[14], int32_t& prim) {
+  const double2* __restrict__ q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) { const double2 a = __ldg(q + i); w[2 * i] = a.x; w[2 * i + 1] = a.y; }
+  prim = __ldg(reinterpret_cast<const int32_t*>(p) + 28);
+}
+// myTriangle.intersectCheck on a packed record: the same operations, in the same order, as primTest's PT_TRI case
+__device__ __forceinline__ bool triTestPacked(const double (&w)[14], const Ray& r, double& tOut, int& stOut) {
+  D3 N = d3(w[9], w[10], w[11]); double D = w[12];
+  double planeRes = dot3(N, r.d);
+  if (!(fabs(planeRes) > 0)) return false;
+  int st = 0;
+  if (planeRes > 0) { st = 1; N = d3(-N.x, -N.y, -N.z); D = w[13]; planeRes = dot3(N, r.d); if (!(fabs(planeRes) > 0) || planeRes > 0) return false; }
+  const double t = -(dot3(N, r.o) + D) / planeRes;
+  if (!(t > DRT_EPS)) return false;
+  const D3 p = pointOnRay(r, t);
+  const D3 a = d3(w[0], w[1], w[2]), b = d3(w[3], w[4], w[5]), c = d3(w[6], w[7], w[8]);
+  const D3 V0 = st ? c : a, V2 = st ? a : c;                       // reversed winding: vertices (c, b, a)
+  { D3 ir = d3(p.x - V0.x, p.y - V0.y, p.z - V0.z), e = d3(V0.x - V2.x, V0.y - V2.y, V0.z - V2.z); if (dot3(cross3(ir, e), N) < -DRT_EPS) return false; }
+  { D3 ir = d3(p.x - b.x, p.y - b.y, p.z - b.z), e = d3(b.x - V0.x, b.y - V0.y, b.z - V0.z); if (dot3(cross3(ir, e), N) < -DRT_EPS) return false; }
+  { D3 ir = d3(p.x - V2.x, p.y - V2.y, p.z - V2.z), e = d3(V2.x - b.x, V2.y - b.y, V2.z - b.z); if (dot3(cross3(ir, e), N) < -DRT_EPS) return false; }
+  tOut = t; stOut = st; return true;
+}
+// both child boxes of a node with 128-bit loads
+__device__ __forceinline__ void ldNode(const FNode* __restrict__ p, double (&bx)[12], int32_t& left, int32_t& right, int32_t& triL, int32_t& triR) {
+  const double2* __restrict__ q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { const double2 a = __ldg(q + i); bx[2 * i] = a.x; bx[2 * i + 1] = a.y; }
+  const int4 l = __ldg(reinterpret_cast<const int4*>(p) + 6); left = l.x; right = l.y; triL = l.z; triR = l.w;
+}
+// conventional conservative slab test (LBVH mode only): a ray that starts inside the box enters it at t = 0
+__device__ __forceinline__ bool boxTestStd(const double* mn, const double* mx, const Ray& r, const D3& inv, double& tEntry) {
+  double t0 = (mn[0] - r.o.x) * inv.x, t1 = (mx[0] - r.o.x) * inv.x; double tn = fmin(t0, t1), tf = fmax(t0, t1);
+  t0 = (mn[1] - r.o.y) * inv.y; t1 = (mx[1] - r.o.y) * inv.y; tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));
+  t0 = (mn[2] - r.o.z) * inv.z; t1 = (mx[2] - r.o.z) * inv.z; tn = fmax(tn, fmin(t0, t1)); tf = fmin(tf, fmax(t0, t1));
+  tEntry = fmax(tn, 0.0); return tf >= tEntry;
+}
+
+#define DRT_FSTACK 64
+struct FEntry { int32_t ref; int32_t tri; float te; };      // ref >= 0 inner node, else leaf with tri code; te rounded DOWN (pruning stays conservative)
+
+// Closest hit inside one fast BVH (root box already accepted by the caller). `trans` is the ray the boxes are tested with,
+// `r` the ray the triangles are tested with (see SURVEY Q7 for why they can differ).  Result: the minimum-t hit over every leaf
+// whose chain of boxes is accepted -- the set the reference's left-first recursion searches; equal-t candidates resolve to the
+// lower FTri index, i.e. the reference's visiting order.
+template <bool STD_BOX>
+__device__ __forceinline__ bool fastClosest(const DScene& S, const FBvh& B, const Ray& trans, const Ray& r, D3 rawDir, Hit& out, TraceCounters* tc) {
+  const D3 inv = rayInv(trans);
+  FEntry stack[DRT_FSTACK]; int sp = 0;
+  double bestT = DRT_DMAX; int bestTri = -1, bestSt = 0;
+  int32_t ref = B.fastRoot, tri = -1;
+  while (true) {
+    if (ref >= 0) {
+      double bx[12]; int32_t left, right, triL, triR; ldNode(S.fnodes + ref, bx, left, right, triL, triR);
+      double teL, teR; if (tc) tc->box += 2;
+      bool hl = STD_BOX ? boxTestStd(bx, bx + 3, trans, inv, teL) : boxTestFx(bx, bx + 3, trans, inv, teL);
+      bool hr = STD_BOX ? boxTestStd(bx + 6, bx + 9, trans, inv, teR) : boxTestFx(bx + 6, bx + 9, trans, inv, teR);
+      hl = hl && teL < bestT; hr = hr && teR < bestT;
+      if (hl && hr) {
+        const bool rightFirst = teR < teL;
+        FEntry e; e.ref = rightFirst ? left : right; e.tri = rightFirst ? triL : triR; e.te = __double2float_rd(rightFirst ? teL : teR);
+        if (sp < DRT_FSTACK) stack[sp++] = e;
+        ref = rightFirst ? right : left; tri = rightFirst ? triR : triL; continue;
+      }
+      if (hl) { ref = left; tri = triL; continue; }
+      if (hr) { ref = right; tri = triR; continue; }
+    } else {
+      const int cnt = tri & 7; const int first = tri >> 3;
+      for (int i = 0; i < cnt; ++i) {
+        double w[14]; int32_t prim; ldTri(S.tris + first + i, w, prim); (void)prim;
+        double t; int st; if (tc) ++tc->prim;
+        if (triTestPacked(w, r, t, st) && (t < bestT || (t == bestT && first + i < bestTri))) { bestT = t; bestTri = first + i; bestSt = st; }
+      }
+    }
+    // pop
+    while (true) {
+      if (sp == 0) {
+        if (bestTri < 0) return false;
+        out.t = bestT; out.prim = S.tris[bestTri].prim; out.arg0 = 0; out.arg1 = 0; out.state = bestSt; out.hitXform = B.triHitXform; out.shaderOverride = -1; out.inst = -1;
+        out.loc = pointOnRay(r, bestT); out.rawDir = rawDir; return true;
+      }
+      const FEntry e = stack[--sp];
+      if ((double)e.te < bestT) { ref = e.ref; tri = e.tri; break; }
+    }
+  }
+}
+// Any hit inside one fast BVH: (dist - t) > eps for a triangle, every box on the way accepted with (dist - entry) > eps
+template <bool STD_BOX>
+__device__ __forceinline__ bool fastShadow(const DScene& S, const FBvh& B, const Ray& trans, const Ray& r, double dist, TraceCounters* tc) {
+  const D3 inv = rayInv(trans);
+  FEntry stack[DRT_FSTACK]; int sp = 0;
+  int32_t ref = B.fastRoot, tri = -1;
+  while (true) {
+    if (ref >= 0) {
+      double bx[12]; int32_t left, right, triL, triR; ldNode(S.fnodes + ref, bx, left, right, triL, triR);
+      double teL, teR; if (tc) tc->box += 2;
+      bool hl = (STD_BOX ? boxTestStd(bx, bx + 3, trans, inv, teL) : boxTestFx(bx, bx + 3, trans, inv, teL)) && (dist - teL) > DRT_EPS;
+      bool hr = (STD_BOX ? boxTestStd(bx + 6, bx + 9, trans, inv, teR) : boxTestFx(bx + 6, bx + 9, trans, inv, teR)) && (dist - teR) > DRT_EPS;
+      if (hl && hr) { FEntry e; e.ref = right; e.tri = triR; e.te = 0; if (sp < DRT_FSTACK) stack[sp++] = e; ref = left; tri = triL; continue; }
+      if (hl) { ref = left; tri = triL; continue; }
+      if (hr) { ref = right; tri = triR; continue; }
+    } else {
+      const int cnt = tri & 7; const int first = tri >> 3;
+      for (int i = 0; i < cnt; ++i) {
+        double w[14]; int32_t prim; ldTri(S.tris + first + i, w, prim); (void)prim;
+        double t; int st; if (tc) ++tc->prim;
+        if (triTestPacked(w, r, t, st) && (dist - t) > DRT_EPS) return true;
+      }
+    }
+    if (sp == 0) return false;
+    const FEntry e = stack[--sp]; ref = e.ref; tri = e.tri;
+  }
+}
+// may this BVH be searched out of the reference's order for this pair of rays?  (through an instance the triangles see a
+// re-normalised direction, so hit t and box-entry t are in different units; pruning stays conservative only if the local direction
+// was at least unit length)
+__device__ __forceinline__ bool fastUsable(const DScene& S, const FBvh& B, double localDirLen2) { return S.accelMode != 0 && B.fast != 0 && localDirLen2 >= 1.0; }
+
 #define DRT_STACK 48
 struct Frame { int32_t node; double tL; };     // node >= 0: "after left" of that node; node == -1: "after right", tL saved
 
@@ -259,6 +380,13 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
   const FBvh& B = S.bvhs[idx];
   if (tc) ++tc->box;
   if (!boxTest(B.bmin, B.bmax, trans, te, face)) return false;
+  if (S.accelMode != 0 && B.fast != 0) {
+    const double len2 = _ray.norm ? 1.0 : dot3(_ray.d, _ray.d);
+    if (fastUsable(S, B, len2)) {
+      const Ray r = xfRay(_ray, S.xforms[B.triXform].inv);          // what every leaf child of this mesh would be tested with
+      return (S.accelMode == 2) ? fastClosest<true>(S, B, trans, r, _ray.d, out, tc) : fastClosest<false>(S, B, trans, r, _ray.d, out, tc);
+    }
+  }
   const D3 inv = rayInv(trans);
   XfCache xc; xc.xf = -1;
   Hit& best = out; hitReset(best);
@@ -360,6 +488,10 @@ __device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const
   XfCache xc; xc.xf = -1;
   if (kind == OK_LIST) return listShadow<LVL>(S, idx, _ray, trans, inv, time, dist, tc, xc);
   const FBvh& B = S.bvhs[idx];
+  if (S.accelMode != 0 && B.fast != 0) {                              // any-hit does not depend on the visiting order
+    const Ray r = xfRay(_ray, S.xforms[B.triXform].inv);
+    return (S.accelMode == 2) ? fastShadow<true>(S, B, trans, r, dist, tc) : fastShadow<false>(S, B, trans, r, dist, tc);
+  }
   int32_t stack[DRT_STACK]; int sp = 0; int32_t node = B.root;
   double te;
   while (true) {

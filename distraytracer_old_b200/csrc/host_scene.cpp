@@ -512,7 +512,50 @@ void HostScene::command(const std::string& line) {
   } catch (Missing&) { throw std::runtime_error("malformed .cli line: " + line); }
 }
 
+// A leaf qualifies when it holds 1..7 plain triangles that all use (triXform, triHitXform) and whose reversed winding state carries
+// exactly the negated normal. Returns the tri-leaf code or -1.
+int32_t HostScene::packLeaf(const FList& L, int triXform, int triHitXform) {
+  if (L.childCount < 1 || L.childCount > 7) return -1;
+  const size_t start = tris.size();
+  for (int i = 0; i < L.childCount; ++i) {
+    const FObjRef& c = children[L.childStart + i];
+    if (c.kind != OK_PRIM || c.xform != triXform || c.hitXform != triHitXform || prims[c.idx].type != PT_TRI) { tris.resize(start); return -1; }
+    const double* q = pdata.data() + prims[c.idx].data; const double* r = q + DRT_TRI_STATE;
+    FTri T; std::memset(&T, 0, sizeof(T));
+    for (int k = 0; k < 9; ++k) T.v[k] = q[k];
+    for (int k = 0; k < 3; ++k) T.N[k] = q[9 + k];
+    T.D = q[12]; T.Drev = r[12]; T.prim = c.idx;
+    bool ok = true;
+    for (int k = 0; k < 3; ++k) { double neg = -q[9 + k]; if (std::memcmp(&neg, &r[9 + k], 8) != 0 && !(neg == 0 && r[9 + k] == 0)) ok = false; }
+    for (int k = 0; k < 9; ++k) if (r[k] != q[3 * (2 - k / 3) + k % 3]) ok = false;
+    if (!ok) { tris.resize(start); return -1; }
+    tris.push_back(T);
+  }
+  return (int32_t)((start << 3) | (size_t)L.childCount);
+}
+void HostScene::buildFastBvh(FBvh& B) {
+  B.fast = 0; B.triXform = B.triHitXform = -1; B.fastRoot = B.root; B.triStart = (int)tris.size(); B.triCount = 0;
+  if (B.root < 0) return;                                   // a single leaf: nothing to accelerate
+  // first leaf decides the shared CTMs
+  int32_t n = B.root; while (n >= 0) n = nodes[n].left;
+  const FList& L0 = lists[~n]; if (L0.childCount < 1) return;
+  const FObjRef& c0 = children[L0.childStart]; const int tx = c0.xform, thx = c0.hitXform;
+  const size_t triMark = tris.size();
+  // DFS, left first: FTri index order == the reference's visiting order (used as the tie-break of the fast traversal)
+  // (simple recursive walk: depth is O(log n) for the median-split tree)
+  struct Walk { HostScene* h; int tx, thx; bool ok = true;
+    void go(int32_t r) { if (!ok) return; FNode& nd = h->nodes[r]; nd.triL = nd.triR = -1;
+      if (nd.left >= 0) go(nd.left); else { nd.triL = h->packLeaf(h->lists[~nd.left], tx, thx); if (nd.triL < 0) ok = false; }
+      if (!ok) return;
+      if (nd.right >= 0) go(nd.right); else { nd.triR = h->packLeaf(h->lists[~nd.right], tx, thx); if (nd.triR < 0) ok = false; } } } w{this, tx, thx};
+  w.go(B.root);
+  if (!w.ok) { tris.resize(triMark); struct Clr { HostScene* h; void go(int32_t r) { FNode& nd = h->nodes[r]; nd.triL = nd.triR = -1; if (nd.left >= 0) go(nd.left); if (nd.right >= 0) go(nd.right); } } c{this}; c.go(B.root); return; }
+  B.fast = 1; B.triXform = tx; B.triHitXform = thx; B.triStart = (int)triMark; B.triCount = (int)(tris.size() - triMark);
+}
+
 void HostScene::finalize() {
+  tris.clear();
+  for (FBvh& B : bvhs) buildFastBvh(B);
   top.clear();
   for (const HGeom& gm : topGeoms_) { FObjRef r; r.kind = gm.kind; r.idx = gm.idx; r.xform = gm.xform; r.hitXform = gm.xform; top.push_back(r); }
   g.numTop = (int)top.size(); g.numLights = (int)lights.size();

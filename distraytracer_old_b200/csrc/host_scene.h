@@ -47,6 +47,7 @@ class HostScene {
   std::vector<FList> lists;
   std::vector<FBvh> bvhs;
   std::vector<FNode> nodes;
+  std::vector<FTri> tris;             // packed triangles of the fast BVHs (see scene_flat.h)
   std::vector<FLight> lights;
   std::vector<FShader> shaders;
   std::vector<FTexture> textures;
@@ -108,6 +109,8 @@ class HostScene {
   void readFile(const std::string& file, bool isMain);
   int primSerial_ = 0, instSerial_ = 0;
   void dumpNode(int32_t ref, std::vector<int32_t>& out) const;
+  void buildFastBvh(FBvh& B);          // packed triangle records + tri-leaf codes when the BVH qualifies
+  int32_t packLeaf(const FList& L, int triXform, int triHitXform);
 };
 
 }  // namespace drt

@@ -361,7 +361,7 @@ void Renderer::upload(const HostScene& hs) {
   DScene& d = impl_->ds; auto& ow = impl_->owned;
   d.xforms = uploadVec(hs.xforms, ow, st); d.prims = uploadVec(hs.prims, ow, st); d.pdata = uploadVec(hs.pdata, ow, st); d.top = uploadVec(hs.top, ow, st);
   d.children = uploadVec(hs.children, ow, st); d.instances = uploadVec(hs.instances, ow, st); d.lists = uploadVec(hs.lists, ow, st); d.bvhs = uploadVec(hs.bvhs, ow, st);
-  d.nodes = uploadVec(hs.nodes, ow, st); d.lights = uploadVec(hs.lights, ow, st); d.shaders = uploadVec(hs.shaders, ow, st); d.textures = uploadVec(hs.textures, ow, st);
+  d.nodes = uploadVec(hs.nodes, ow, st); d.tris = uploadVec(hs.tris, ow, st); d.fnodes = d.nodes; d.accelMode = traceMode_ & 3; d.padA = 0; d.lights = uploadVec(hs.lights, ow, st); d.shaders = uploadVec(hs.shaders, ow, st); d.textures = uploadVec(hs.textures, ow, st);
   d.texColors = uploadVec(hs.texColors, ow, st); d.images = uploadVec(hs.images, ow, st); d.texels = uploadVec(hs.texels, ow, st);
   impl_->sceneBytes = hs.xforms.size() * sizeof(FXform) + hs.prims.size() * sizeof(FPrim) + hs.pdata.size() * 8 + hs.children.size() * sizeof(FObjRef) + hs.nodes.size() * sizeof(FNode) + hs.lists.size() * sizeof(FList) + hs.texels.size() * 4;
   d.g = hs.g; d.g.pad0 = 0;

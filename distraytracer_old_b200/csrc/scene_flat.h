@@ -40,10 +40,18 @@ struct FInstance { int32_t baseKind, baseIdx, xform, shader, serial, pad0, pad1,
 struct FList { int32_t xform, childStart, childCount, pad; double bmin[3], bmax[3]; };
 
 // myBVH root (myGeomBase.java:309-423). root >= 0: inner node index; root < 0: ~list index (single leaf)
-struct FBvh { int32_t xform, root, nodeCount, dropped; double bmin[3], bmax[3]; };
+// "fast" BVHs (every leaf holds only triangles that share one CTM) additionally own a contiguous run of packed triangle records
+// (FTri, DFS leaf order) and tri-leaf codes in their nodes; fastRoot indexes DScene::fnodes (the same nodes in reference-topology
+// modes, the GPU-built LBVH nodes in DRT_ACCEL_LBVH mode).
+struct FBvh { int32_t xform, root, nodeCount, dropped; double bmin[3], bmax[3]; int32_t fast, triXform, triHitXform, fastRoot, triStart, triCount, pad0, pad1; };
 
 // inner node with both child boxes; child >= 0 inner node, child < 0 -> ~list index. 128 B, 16 B aligned (128-bit loads).
-struct alignas(16) FNode { double lmin[3], lmax[3], rmin[3], rmax[3]; int32_t left, right, pad0, pad1; int32_t pad2[4]; };
+// triL / triR: when the child is a pure-triangle leaf of a fast BVH, (first FTri index << 3) | count ; else -1.
+struct alignas(16) FNode { double lmin[3], lmax[3], rmin[3], rmax[3]; int32_t left, right, triL, triR; int32_t pad2[4]; };
+
+// packed triangle of a fast BVH, 128 B, read with 8 x 128-bit loads. Winding state 0 as given; state 1 (myPlanarObject.invertNormal,
+// :71-88) = vertices in reverse order, normal -N (bitwise), plane offset Drev (formed from the reversed first vertex, so stored).
+struct alignas(16) FTri { double v[9]; double N[3]; double D, Drev; int32_t prim, pad[3]; };
 
 enum LightType : int32_t { LT_POINT = 0, LT_SPOT = 1, LT_DISK = 2 };
 struct FLight {

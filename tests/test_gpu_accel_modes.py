@@ -1,0 +1,66 @@
+"""GPU tests of the traversal modes: DRT_ACCEL_REFERENCE_FAST must reproduce DRT_ACCEL_REFERENCE bit for bit
+(same tree, same box rule, same triangle arithmetic; only the visiting order and the pruning differ), and DRT_ACCEL_LBVH must keep
+primary-ray hit IDs exact while its mesh self-shadowing differs by construction -- that difference is measured here."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MESH_SCENES = ["p3_t08", "p3_t09", "p3_t10", "p3_t11", "p3_t11_sierp", "p4_t06", "plnts3ColsBunnies", "p3_t12", "p3_t05"]
+
+
+def render(drt, make, name, accel, cols, rows, spp=0, **kw):
+    ctx = make(cols, rows, **kw)
+    s = drt.Scene.from_cli(ctx, name + ".cli", spp=spp, accel=accel)
+    g = s.draw(aov=True)
+    info = s.info()
+    ctx.close()
+    return g, info
+
+
+@pytest.mark.parametrize("name", MESH_SCENES)
+def test_fast_mode_equals_reference_mode(drt, gpu_ctx_factory, name):
+    spp = 2 if name == "plnts3ColsBunnies" else 0
+    a, _ = render(drt, gpu_ctx_factory, name, drt.ACCEL_REFERENCE, 320, 240, spp)
+    b, _ = render(drt, gpu_ctx_factory, name, drt.ACCEL_REFERENCE_FAST, 320, 240, spp)
+    assert np.array_equal(a["hit_prim"], b["hit_prim"]) and np.array_equal(a["hit_inst"], b["hit_inst"])
+    assert np.array_equal(a["t"], b["t"])
+    assert np.array_equal(a["argb"], b["argb"])
+    for k in ("rays_primary", "rays_shadow", "rays_reflect", "rays_refract"):
+        assert getattr(a["stats"], k) == getattr(b["stats"], k)
+
+
+def test_fast_mode_matches_oracle(drt, orc, gpu_ctx_factory):
+    for name in ("p3_t09", "p3_t11_sierp"):
+        g, _ = render(drt, gpu_ctx_factory, name, drt.ACCEL_REFERENCE_FAST, 160, 160)
+        r = orc.OracleScene(name + ".cli", cols=160, rows=160).render(threads=os.cpu_count())
+        assert (g["hit_prim"] != r["hit_prim"]).sum() <= 2 and (g["hit_inst"] != r["hit_inst"]).sum() <= 2
+        d = np.abs(orc.argb_to_rgb8(g["argb"]).astype(int) - orc.argb_to_rgb8(r["argb"]).astype(int)).max(axis=-1)
+        assert (d > 2).mean() <= 1e-3
+
+
+def test_fast_mode_counters_do_less_work(drt, gpu_ctx_factory):
+    a, _ = render(drt, gpu_ctx_factory, "p3_t09", drt.ACCEL_REFERENCE, 320, 240, counters=True)
+    b, _ = render(drt, gpu_ctx_factory, "p3_t09", drt.ACCEL_REFERENCE_FAST, 320, 240, counters=True)
+    assert b["stats"].prim_tests_closest <= a["stats"].prim_tests_closest
+    assert np.array_equal(a["argb"], b["argb"])
+
+
+def test_fast_mode_explicit_rays_from_everywhere(drt, gpu_ctx_factory):
+    """Rays starting inside / on / outside the meshes' boxes: closest-hit IDs and t must be identical in both modes."""
+    rng = np.random.default_rng(3)
+    for name in ("p3_t09", "p3_t10", "p3_t11_sierp"):
+        n = 200000
+        org = rng.uniform(-3, 3, size=(n, 3)); org[:, 2] -= 3
+        d = rng.normal(size=(n, 3))
+        res = []
+        for accel in (drt.ACCEL_REFERENCE, drt.ACCEL_REFERENCE_FAST):
+            ctx = gpu_ctx_factory()
+            s = drt.Scene.from_cli(ctx, name + ".cli", accel=accel)
+            res.append(s.trace_rays(org, d))
+            ctx.close()
+        assert np.array_equal(res[0][0], res[1][0]), name
+        assert np.array_equal(res[0][1], res[1][1]), name
+        assert (res[0][0][:, 0] >= 0).sum() > 1000
