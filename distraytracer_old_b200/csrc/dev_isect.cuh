@@ -201,7 +201,7 @@ __device__ __forceinline__ void ldTri(const FTri* __restrict__ p, double (&w)[14
   const double2* __restrict__ q = reinterpret_cast<const double2*>(p);
 #pragma unroll
   for (int i = 0; i < 7; ++i) { const double2 a = __ldg(q + i); w[2 * i] = a.x; w[2 * i + 1] = a.y; }
-  prim = __ldg(reinterpret_cast<const int32_t*>(p) + 28);
+  prim = __ldg(reinterpret_cast<const int32_t*>(p) + 29);      // rank in the reference's visiting order (FTri::pad[0])
 }
 // myTriangle.intersectCheck on a packed record: the same operations, in the same order, as primTest's PT_TRI case
 __device__ __forceinline__ bool triTestPacked(const double (&w)[14], const Ray& r, double& tOut, int& stOut) {
@@ -246,7 +246,7 @@ template <bool STD_BOX>
 __device__ __forceinline__ bool fastClosest(const DScene& S, const FBvh& B, const Ray& trans, const Ray& r, D3 rawDir, Hit& out, TraceCounters* tc) {
   const D3 inv = rayInv(trans);
   FEntry stack[DRT_FSTACK]; int sp = 0;
-  double bestT = DRT_DMAX; int bestTri = -1, bestSt = 0;
+  double bestT = DRT_DMAX; int bestTri = -1, bestRank = 0x7fffffff, bestSt = 0;
   int32_t ref = B.fastRoot, tri = -1;
   while (true) {
     if (ref >= 0) {
@@ -266,9 +266,9 @@ __device__ __forceinline__ bool fastClosest(const DScene& S, const FBvh& B, cons
     } else {
       const int cnt = tri & 7; const int first = tri >> 3;
       for (int i = 0; i < cnt; ++i) {
-        double w[14]; int32_t prim; ldTri(S.tris + first + i, w, prim); (void)prim;
+        double w[14]; int32_t rank; ldTri(S.tris + first + i, w, rank);
         double t; int st; if (tc) ++tc->prim;
-        if (triTestPacked(w, r, t, st) && (t < bestT || (t == bestT && first + i < bestTri))) { bestT = t; bestTri = first + i; bestSt = st; }
+        if (triTestPacked(w, r, t, st) && (t < bestT || (t == bestT && rank < bestRank))) { bestT = t; bestTri = first + i; bestRank = rank; bestSt = st; }
       }
     }
     // pop

@@ -524,7 +524,7 @@ int32_t HostScene::packLeaf(const FList& L, int triXform, int triHitXform) {
     FTri T; std::memset(&T, 0, sizeof(T));
     for (int k = 0; k < 9; ++k) T.v[k] = q[k];
     for (int k = 0; k < 3; ++k) T.N[k] = q[9 + k];
-    T.D = q[12]; T.Drev = r[12]; T.prim = c.idx;
+    T.D = q[12]; T.Drev = r[12]; T.prim = c.idx; T.pad[0] = (int32_t)tris.size();   // pad[0] = rank in the reference's visiting order
     bool ok = true;
     for (int k = 0; k < 3; ++k) { double neg = -q[9 + k]; if (std::memcmp(&neg, &r[9 + k], 8) != 0 && !(neg == 0 && r[9 + k] == 0)) ok = false; }
     for (int k = 0; k < 9; ++k) if (r[k] != q[3 * (2 - k / 3) + k % 3]) ok = false;

@@ -291,6 +291,7 @@ __global__ void k_eval_texture(const __grid_constant__ DScene S, int shader, lon
 }  // namespace drt
 
 #include "photon.cuh"
+#include "lbvh.cuh"
 
 namespace drt {
 
@@ -322,6 +323,7 @@ struct Renderer::Impl {
   cudaEvent_t ev[8];
   PhotonMap photons;
   size_t sceneBytes = 0;
+  float lbvhMs = 0; long long lbvhTris = 0, lbvhNodes = 0;
 };
 
 Renderer::Renderer(int device) : impl_(new Impl), device_(device) {
@@ -360,10 +362,33 @@ void Renderer::upload(const HostScene& hs) {
   }
   DScene& d = impl_->ds; auto& ow = impl_->owned;
   d.xforms = uploadVec(hs.xforms, ow, st); d.prims = uploadVec(hs.prims, ow, st); d.pdata = uploadVec(hs.pdata, ow, st); d.top = uploadVec(hs.top, ow, st);
-  d.children = uploadVec(hs.children, ow, st); d.instances = uploadVec(hs.instances, ow, st); d.lists = uploadVec(hs.lists, ow, st); d.bvhs = uploadVec(hs.bvhs, ow, st);
-  d.nodes = uploadVec(hs.nodes, ow, st); d.tris = uploadVec(hs.tris, ow, st); d.fnodes = d.nodes; d.accelMode = traceMode_ & 3; d.padA = 0; d.lights = uploadVec(hs.lights, ow, st); d.shaders = uploadVec(hs.shaders, ow, st); d.textures = uploadVec(hs.textures, ow, st);
+  d.children = uploadVec(hs.children, ow, st); d.instances = uploadVec(hs.instances, ow, st); d.lists = uploadVec(hs.lists, ow, st);
+  d.nodes = uploadVec(hs.nodes, ow, st); d.tris = uploadVec(hs.tris, ow, st); d.fnodes = d.nodes; d.accelMode = traceMode_ & 3; d.padA = 0;
+  // DRT_ACCEL_LBVH: rebuild every qualifying pure-triangle BVH on the GPU (see lbvh.cuh). The reference-topology nodes stay resident
+  // (instance-level trees, BVHs that do not qualify, and rays whose units forbid reordering still use them).
+  std::vector<FBvh> bv = hs.bvhs; impl_->lbvhMs = 0; impl_->lbvhTris = 0; impl_->lbvhNodes = 0;
+  if (d.accelMode == 2) {
+    size_t extra = 0; for (const FBvh& B : bv) if (B.fast && B.triXform == B.xform && B.triCount > 4) extra += (size_t)((B.triCount + 3) / 4 - 1);
+    if (extra) {
+      const size_t n0 = hs.nodes.size(); FNode* ln = nullptr; FTri* lt = nullptr;
+      CK(cudaMalloc(&ln, (n0 + extra) * sizeof(FNode))); ow.push_back(ln); CK(cudaMalloc(&lt, (hs.tris.size() ? hs.tris.size() : 1) * sizeof(FTri))); ow.push_back(lt);
+      if (n0) CK(cudaMemcpyAsync(ln, d.nodes, n0 * sizeof(FNode), cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(lt, d.tris, hs.tris.size() * sizeof(FTri), cudaMemcpyDeviceToDevice, st));
+      cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventRecord(e0, st));
+      size_t at = n0; LbvhScratch sc;
+      for (FBvh& B : bv) if (B.fast && B.triXform == B.xform && B.triCount > 4) {
+        const int wrote = lbvhBuild(lt, B.triStart, B.triCount, B.bmin, B.bmax, ln + at, (int)at, sc, st);
+        if (wrote > 0) { B.fastRoot = (int32_t)at; at += (size_t)wrote; impl_->lbvhTris += B.triCount; impl_->lbvhNodes += wrote; }
+      }
+      CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError()); CK(cudaEventElapsedTime(&impl_->lbvhMs, e0, e1));
+      cudaEventDestroy(e0); cudaEventDestroy(e1); sc.release();
+      d.fnodes = ln; d.tris = lt;
+    }
+  }
+  d.bvhs = uploadVec(bv, ow, st); CK(cudaStreamSynchronize(st));      // bv is a local: finish the copy before it goes away
+  d.lights = uploadVec(hs.lights, ow, st); d.shaders = uploadVec(hs.shaders, ow, st); d.textures = uploadVec(hs.textures, ow, st);
   d.texColors = uploadVec(hs.texColors, ow, st); d.images = uploadVec(hs.images, ow, st); d.texels = uploadVec(hs.texels, ow, st);
-  impl_->sceneBytes = hs.xforms.size() * sizeof(FXform) + hs.prims.size() * sizeof(FPrim) + hs.pdata.size() * 8 + hs.children.size() * sizeof(FObjRef) + hs.nodes.size() * sizeof(FNode) + hs.lists.size() * sizeof(FList) + hs.texels.size() * 4;
+  impl_->sceneBytes = hs.xforms.size() * sizeof(FXform) + hs.prims.size() * sizeof(FPrim) + hs.pdata.size() * 8 + hs.children.size() * sizeof(FObjRef) + hs.nodes.size() * sizeof(FNode) + hs.tris.size() * sizeof(FTri) + hs.lists.size() * sizeof(FList) + hs.texels.size() * 4;
   d.g = hs.g; d.g.pad0 = 0;
   for (const FPrim& p : hs.prims) if (p.type == PT_MOVSPHERE) d.g.pad0 = 1;
   d.numPhotons = 0; d.phPos = nullptr; d.phPwr = nullptr; d.cellStart = nullptr; d.cellEnd = nullptr;
@@ -488,6 +513,7 @@ void Renderer::probePhotons(long long n, const double* ptsHost, double* out5Host
   CK(cudaMemcpyAsync(out5Host, b, n * 40, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
   cudaFree(a); cudaFree(b);
 }
+void Renderer::accelInfo(double out[4]) const { out[0] = impl_->lbvhMs; out[1] = (double)impl_->lbvhTris; out[2] = (double)impl_->lbvhNodes; out[3] = (double)impl_->sceneBytes; }
 long long Renderer::getPhotons(double* out6Host, long long cap) { CK(cudaSetDevice(device_)); return impl_->photons.download(out6Host, cap, (cudaStream_t)stream_); }
 
 void Renderer::traceRays(long long n, const double* orgHost, const double* dirHost, int32_t* idsHost, double* tHost) {

@@ -39,6 +39,7 @@ class Renderer {
   long long exportPhotonsDevice(double* dst6Dev, long long cap);                  // canonical-order records -> caller's device buffer; returns count
   void buildPhotonsFromDevice(const double* src6Dev, long long n, RenderStats* stats);   // replace the record set (e.g. all-gathered) and build the grid
   void probePhotons(long long n, const double* ptsHost, double* out5Host);       // per point: sum r,g,b of the k nearest, d^2 of the farthest, candidates visited
+  void accelInfo(double out[4]) const;                 // LBVH build ms (CUDA events), triangles and nodes it covers, scene bytes in HBM
   int cols() const { return g_.cols; }
   int rows() const { return g_.rows; }
   int spp() const { return g_.spp; }

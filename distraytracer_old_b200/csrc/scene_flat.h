@@ -51,7 +51,7 @@ struct alignas(16) FNode { double lmin[3], lmax[3], rmin[3], rmax[3]; int32_t le
 
 // packed triangle of a fast BVH, 128 B, read with 8 x 128-bit loads. Winding state 0 as given; state 1 (myPlanarObject.invertNormal,
 // :71-88) = vertices in reverse order, normal -N (bitwise), plane offset Drev (formed from the reversed first vertex, so stored).
-struct alignas(16) FTri { double v[9]; double N[3]; double D, Drev; int32_t prim, pad[3]; };
+struct alignas(16) FTri { double v[9]; double N[3]; double D, Drev; int32_t prim, pad[3]; };   // pad[0] = rank in the reference's DFS order (tie-break)
 
 enum LightType : int32_t { LT_POINT = 0, LT_SPOT = 1, LT_DISK = 2 };
 struct FLight {

@@ -61,6 +61,7 @@ int drt_scene_load_cli(drt_ctx* ctx, const char* file, const char* data_dir); /*
 int drt_scene_override(drt_ctx* ctx, int32_t spp, int64_t photons); /* <=0 / <0 keep the file's values */
 int drt_scene_finalize(drt_ctx* ctx, int32_t accel_mode);        /* flatten, build acceleration structures, upload to HBM */
 int drt_scene_reupload(drt_ctx* ctx);                            /* host->device copy of the flattened scene again (used by end-to-end timing) */
+int drt_accel_info(drt_ctx* ctx, double* out4);                  /* after finalize: GPU LBVH build ms, triangles and nodes it covers, scene bytes resident in HBM */
 int drt_scene_info(drt_ctx* ctx, int32_t* out16);                /* cols, rows, spp, top objects, lights, prims, instances, photon kind, shaders, nodes, xforms, lists, ... */
 
 /* ---- rendering: replaces myScene.initRender + draw; argb layout == PImage.pixels ---- */
