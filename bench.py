@@ -111,7 +111,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--accel", type=int, default=int(os.environ.get("DRT_ACCEL", "0")))
+    ap.add_argument("--accel", type=int, default=int(os.environ.get("DRT_ACCEL", "1")), help="0 reference-topology literal order, 1 reference-topology near-first (bit-identical results, default), 2 GPU LBVH")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -181,9 +181,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         host = torch.empty(npix, dtype=torch.int32).pin_memory()
-        scene_bytes = 0
-        info = scene.info()
-        scene_bytes = info["xforms"] * 384 + info["prims"] * 32 + info["nodes"] * 128 + info["lists"] * 64 + info["prims"] * 38 * 8
+        scene_bytes = scene.accel_info()["scene_bytes"]            # what drt_scene_reupload copies host -> device
         for _ in range(2):
             scene.reupload(); scene.draw_into(host.data_ptr())
         barrier(); t0 = time.perf_counter(); tot_r = 0
@@ -213,7 +211,8 @@ def main():
         box_per_ray, prim_per_ray = cst.box_tests_closest / r_all, cst.prim_tests_closest / r_all
         closest_share = r_all / cst.rays_total
         cctx.close()
-        bytes_per_ray = 96 + 96 + 64 * box_per_ray + 104 * prim_per_ray               # ray rec in, hit rec out, 64 B per box (128 B node = 2 boxes), 104 B per triangle state
+        tri_bytes = 104 if args.accel == 0 else 128                                  # one winding state of the FP64 pool / one packed 128-byte record
+        bytes_per_ray = 96 + 96 + 64 * box_per_ray + tri_bytes * prim_per_ray           # ray rec in, hit rec out, 64 B per box (128 B node = 2 boxes), triangle bytes
         n_trace_launches = max(1, -(-(npix * w["spp"]) // (8 << 20)))                  # primary-level launches per step (one per batch)
         ms_trace_step = trace_ms / len(gpu_ms)
         closest_rays_per_step = rays * closest_share                                   # primary + reflection + refraction rays of one frame

@@ -88,6 +88,36 @@ __device__ __forceinline__ bool boxTestFx(const double* __restrict__ mn, const d
 }
 __device__ __forceinline__ D3 rayInv(const Ray& r) { return d3(1.0 / r.a.x, 1.0 / r.a.y, 1.0 / r.a.z); }
 
+// Division-free accept/reject of the same rule.  The six slab values formed with the per-ray reciprocal are within 1.5 * 2^-52 (relative)
+// of the quotients the reference forms; min/max selection is 1-Lipschitz, so near_/far_ carry the same bound relative to their own size.
+// Returns 1 (accepted: min(tMax) > max(tMin) and entry > 0, beyond doubt), 0 (rejected beyond doubt) or -1 (inside the error margin, or
+// NaN/inf/denormal operands: the caller runs the exact test).  nearApprox is the entry t to ~3e-16 relative -- good enough to ORDER and
+// PRUNE conservatively, never used where the reference's own value decides something.
+__device__ __forceinline__ int boxQuick(const double* __restrict__ mn, const double* __restrict__ mx, const Ray& r, const D3& inv, double& nearApprox) {
+  const double ax1 = (mn[0] - r.o.x) * inv.x, ax2 = (mx[0] - r.o.x) * inv.x, ay1 = (mn[1] - r.o.y) * inv.y, ay2 = (mx[1] - r.o.y) * inv.y, az1 = (mn[2] - r.o.z) * inv.z, az2 = (mx[2] - r.o.z) * inv.z;
+  const bool sx = ax1 < ax2, sy = ay1 < ay2, sz = az1 < az2;
+  const double tnx = sx ? ax1 : ax2, tfx = sx ? ax2 : ax1, tny = sy ? ay1 : ay2, tfy = sy ? ay2 : ay1, tnz = sz ? az1 : az2, tfz = sz ? az2 : az1;
+  double far_ = tfx; if (tfy < far_) far_ = tfy; if (tfz < far_) far_ = tfz;
+  double near_ = tnx; if (tny > near_) near_ = tny; if (tnz > near_) near_ = tnz;
+  if (!(fabs(near_) > 1e-290) || !(fabs(far_) < 1e290) || !(fabs(near_) < 1e290)) return -1;
+  const double tol = 1e-14 * (fabs(far_) + fabs(near_)), gap = far_ - near_;
+  if (gap > tol) { nearApprox = near_; return near_ > 0 ? 1 : 0; }
+  return (-gap > tol) ? 0 : -1;
+}
+// box accepted?  te = conservative LOWER bound of the entry t (exact when the quick path could not decide)
+__device__ __forceinline__ bool boxAcceptLB(const double* __restrict__ mn, const double* __restrict__ mx, const Ray& r, const D3& inv, double& te) {
+  const int q = boxQuick(mn, mx, r, inv, te);
+  if (q >= 0) { te *= 0.999999999999999; return q != 0; }
+  return boxTestFx(mn, mx, r, inv, te);
+}
+// box accepted AND (dist - entry) > eps, the shadow-ray form (myGeomBase.java:166-170,268-269,397-404)
+__device__ __forceinline__ bool boxAcceptShadow(const double* __restrict__ mn, const double* __restrict__ mx, const Ray& r, const D3& inv, double dist) {
+  double te; const int q = boxQuick(mn, mx, r, inv, te);
+  if (q == 0) return false;
+  if (q > 0) { const double diff = dist - te, m = 1e-13 * (fabs(dist) + fabs(te)); if (diff > DRT_EPS + m) return true; if (diff < DRT_EPS - m) return false; }
+  return boxTestFx(mn, mx, r, inv, te) && (dist - te) > DRT_EPS;
+}
+
 // ---- primitives. `r` is the ray in the primitive's space, rawDir the direction recorded in the hit.
 // Returns true and fills h (t, loc, args, state) on a hit. time: ray time for moving spheres.
 __device__ __noinline__ bool primTest(const DScene& S, int primIdx, const Ray& r, double time, PHit& h) {
@@ -235,36 +265,65 @@ __device__ __forceinline__ bool boxTestStd(const double* mn, const double* mx, c
   tEntry = fmax(tn, 0.0); return tf >= tEntry;
 }
 
+// Traversal stack of the fast paths: the first DRT_SSTACK levels live in shared memory ([level][thread], 8-byte entries, conflict-free),
+// deeper levels (only unbalanced LBVHs get there) in a small local array.  Keeping the stack out of local memory matters: with ~110 k
+// resident threads a per-thread local frame of a few KB is larger than L2 and turns every push/pop into DRAM traffic (profiles/r1b).
+// entry.x = child reference (>= 0 inner node, < 0: ~tri-leaf code), entry.y = bits of the box-entry t rounded DOWN to float.
+#define DRT_TB 128              // threads per block of every kernel that traces
+#ifndef DRT_SSTACK
+#define DRT_SSTACK 0            // levels kept in shared memory; measured on B200 (profiles/r1_tuning.md): shared levels cost more L1 capacity than they save
+#endif
 #define DRT_FSTACK 64
-struct FEntry { int32_t ref; int32_t tri; float te; };      // ref >= 0 inner node, else leaf with tri code; te rounded DOWN (pruning stays conservative)
+#if DRT_SSTACK > 0
+__shared__ uint2 g_fstk[DRT_SSTACK * DRT_TB];
+#endif
+struct FStack {
+  uint2 ovf[DRT_FSTACK - DRT_SSTACK]; int sp = 0;
+  __device__ __forceinline__ void push(int32_t ref, float te) {
+    const uint2 e = make_uint2((uint32_t)ref, __float_as_uint(te));
+#if DRT_SSTACK > 0
+    if (sp < DRT_SSTACK) g_fstk[sp * DRT_TB + threadIdx.x] = e; else
+#endif
+    if (sp < DRT_FSTACK) ovf[sp - DRT_SSTACK] = e;
+    if (sp < DRT_FSTACK) ++sp;
+  }
+  __device__ __forceinline__ uint2 pop() {
+    --sp;
+#if DRT_SSTACK > 0
+    if (sp < DRT_SSTACK) return g_fstk[sp * DRT_TB + threadIdx.x];
+#endif
+    return ovf[sp - DRT_SSTACK];
+  }
+};
+__device__ __forceinline__ int32_t childRef(int32_t link, int32_t triCode) { return link >= 0 ? link : ~triCode; }
 
 // Closest hit inside one fast BVH (root box already accepted by the caller). `trans` is the ray the boxes are tested with,
 // `r` the ray the triangles are tested with (see SURVEY Q7 for why they can differ).  Result: the minimum-t hit over every leaf
 // whose chain of boxes is accepted -- the set the reference's left-first recursion searches; equal-t candidates resolve to the
-// lower FTri index, i.e. the reference's visiting order.
+// lower reference rank, i.e. the reference's visiting order.
 template <bool STD_BOX>
 __device__ __forceinline__ bool fastClosest(const DScene& S, const FBvh& B, const Ray& trans, const Ray& r, D3 rawDir, Hit& out, TraceCounters* tc) {
   const D3 inv = rayInv(trans);
-  FEntry stack[DRT_FSTACK]; int sp = 0;
+  FStack stk;
   double bestT = DRT_DMAX; int bestTri = -1, bestRank = 0x7fffffff, bestSt = 0;
-  int32_t ref = B.fastRoot, tri = -1;
+  int32_t ref = B.fastRoot;
   while (true) {
     if (ref >= 0) {
       double bx[12]; int32_t left, right, triL, triR; ldNode(S.fnodes + ref, bx, left, right, triL, triR);
       double teL, teR; if (tc) tc->box += 2;
-      bool hl = STD_BOX ? boxTestStd(bx, bx + 3, trans, inv, teL) : boxTestFx(bx, bx + 3, trans, inv, teL);
-      bool hr = STD_BOX ? boxTestStd(bx + 6, bx + 9, trans, inv, teR) : boxTestFx(bx + 6, bx + 9, trans, inv, teR);
+      bool hl = STD_BOX ? boxTestStd(bx, bx + 3, trans, inv, teL) : boxAcceptLB(bx, bx + 3, trans, inv, teL);
+      bool hr = STD_BOX ? boxTestStd(bx + 6, bx + 9, trans, inv, teR) : boxAcceptLB(bx + 6, bx + 9, trans, inv, teR);
       hl = hl && teL < bestT; hr = hr && teR < bestT;
+      const int32_t cl = childRef(left, triL), cr = childRef(right, triR);
       if (hl && hr) {
         const bool rightFirst = teR < teL;
-        FEntry e; e.ref = rightFirst ? left : right; e.tri = rightFirst ? triL : triR; e.te = __double2float_rd(rightFirst ? teL : teR);
-        if (sp < DRT_FSTACK) stack[sp++] = e;
-        ref = rightFirst ? right : left; tri = rightFirst ? triR : triL; continue;
+        stk.push(rightFirst ? cl : cr, __double2float_rd(rightFirst ? teL : teR));
+        ref = rightFirst ? cr : cl; continue;
       }
-      if (hl) { ref = left; tri = triL; continue; }
-      if (hr) { ref = right; tri = triR; continue; }
+      if (hl) { ref = cl; continue; }
+      if (hr) { ref = cr; continue; }
     } else {
-      const int cnt = tri & 7; const int first = tri >> 3;
+      const int code = ~ref, cnt = code & 7, first = code >> 3;
       for (int i = 0; i < cnt; ++i) {
         double w[14]; int32_t rank; ldTri(S.tris + first + i, w, rank);
         double t; int st; if (tc) ++tc->prim;
@@ -273,13 +332,13 @@ __device__ __forceinline__ bool fastClosest(const DScene& S, const FBvh& B, cons
     }
     // pop
     while (true) {
-      if (sp == 0) {
+      if (stk.sp == 0) {
         if (bestTri < 0) return false;
         out.t = bestT; out.prim = S.tris[bestTri].prim; out.arg0 = 0; out.arg1 = 0; out.state = bestSt; out.hitXform = B.triHitXform; out.shaderOverride = -1; out.inst = -1;
         out.loc = pointOnRay(r, bestT); out.rawDir = rawDir; return true;
       }
-      const FEntry e = stack[--sp];
-      if ((double)e.te < bestT) { ref = e.ref; tri = e.tri; break; }
+      const uint2 e = stk.pop();
+      if ((double)__uint_as_float(e.y) < bestT) { ref = (int32_t)e.x; break; }
     }
   }
 }
@@ -287,27 +346,28 @@ __device__ __forceinline__ bool fastClosest(const DScene& S, const FBvh& B, cons
 template <bool STD_BOX>
 __device__ __forceinline__ bool fastShadow(const DScene& S, const FBvh& B, const Ray& trans, const Ray& r, double dist, TraceCounters* tc) {
   const D3 inv = rayInv(trans);
-  FEntry stack[DRT_FSTACK]; int sp = 0;
-  int32_t ref = B.fastRoot, tri = -1;
+  FStack stk;
+  int32_t ref = B.fastRoot;
   while (true) {
     if (ref >= 0) {
       double bx[12]; int32_t left, right, triL, triR; ldNode(S.fnodes + ref, bx, left, right, triL, triR);
       double teL, teR; if (tc) tc->box += 2;
-      bool hl = (STD_BOX ? boxTestStd(bx, bx + 3, trans, inv, teL) : boxTestFx(bx, bx + 3, trans, inv, teL)) && (dist - teL) > DRT_EPS;
-      bool hr = (STD_BOX ? boxTestStd(bx + 6, bx + 9, trans, inv, teR) : boxTestFx(bx + 6, bx + 9, trans, inv, teR)) && (dist - teR) > DRT_EPS;
-      if (hl && hr) { FEntry e; e.ref = right; e.tri = triR; e.te = 0; if (sp < DRT_FSTACK) stack[sp++] = e; ref = left; tri = triL; continue; }
-      if (hl) { ref = left; tri = triL; continue; }
-      if (hr) { ref = right; tri = triR; continue; }
+      const bool hl = STD_BOX ? (boxTestStd(bx, bx + 3, trans, inv, teL) && (dist - teL) > DRT_EPS) : boxAcceptShadow(bx, bx + 3, trans, inv, dist);
+      const bool hr = STD_BOX ? (boxTestStd(bx + 6, bx + 9, trans, inv, teR) && (dist - teR) > DRT_EPS) : boxAcceptShadow(bx + 6, bx + 9, trans, inv, dist);
+      const int32_t cl = childRef(left, triL), cr = childRef(right, triR);
+      if (hl && hr) { stk.push(cr, 0.f); ref = cl; continue; }
+      if (hl) { ref = cl; continue; }
+      if (hr) { ref = cr; continue; }
     } else {
-      const int cnt = tri & 7; const int first = tri >> 3;
+      const int code = ~ref, cnt = code & 7, first = code >> 3;
       for (int i = 0; i < cnt; ++i) {
-        double w[14]; int32_t prim; ldTri(S.tris + first + i, w, prim); (void)prim;
+        double w[14]; int32_t rank; ldTri(S.tris + first + i, w, rank);
         double t; int st; if (tc) ++tc->prim;
         if (triTestPacked(w, r, t, st) && (dist - t) > DRT_EPS) return true;
       }
     }
-    if (sp == 0) return false;
-    const FEntry e = stack[--sp]; ref = e.ref; tri = e.tri;
+    if (stk.sp == 0) return false;
+    ref = (int32_t)stk.pop().x;
   }
 }
 // may this BVH be searched out of the reference's order for this pair of rays?  (through an instance the triangles see a

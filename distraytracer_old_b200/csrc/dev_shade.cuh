@@ -34,9 +34,12 @@ __device__ inline D3 primNormal(const DScene& S, const FPrim& P, D3 pt, int arg0
 
 // ---- Perlin noise, float arithmetic
 __device__ __constant__ unsigned char c_perm[512];
+// gradient table {1,1,0},{-1,1,0},{1,-1,0},{-1,-1,0},{1,0,1},{-1,0,1},{1,0,-1},{-1,0,-1},{0,1,1},{0,-1,1},{0,1,-1},{0,-1,-1} (DistRayTracer.java:286)
+// packed 2 bits per component (value + 1) so that the lookup is a shift, not a dynamically indexed local array
 __device__ __forceinline__ float pgrad(int gi, float x, float y, float z) {
-  const int g[12][3] = {{1,1,0},{-1,1,0},{1,-1,0},{-1,-1,0},{1,0,1},{-1,0,1},{1,0,-1},{-1,0,-1},{0,1,1},{0,-1,1},{0,1,-1},{0,-1,-1}};
-  return g[gi][0] * x + g[gi][1] * y + g[gi][2] * z;
+  const uint32_t GX = 0x552222u, GY = 0x22550Au, GZ = 0x0A0A55u; const int sh = 2 * gi;
+  const float gx = (float)((int)((GX >> sh) & 3u) - 1), gy = (float)((int)((GY >> sh) & 3u) - 1), gz = (float)((int)((GZ >> sh) & 3u) - 1);
+  return gx * x + gy * y + gz * z;
 }
 __device__ __forceinline__ float pmix(float a, float b, float t) { return (1 - t) * a + t * b; }
 __device__ __forceinline__ float pfade(float t) { return t * t * t * (t * (t * 6 - 15) + 10); }

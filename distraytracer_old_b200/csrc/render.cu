@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene S,
                                                SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, RayRec* __restrict__ nextRays, NodeRec* __restrict__ nextNodes,
                                                Counters* ctr, long long nextCap) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int nChild = 0; RayRec ch[2]; NodeRec cn[2];
+  // up to two children per hit: A = refraction (slot 1), B = reflection (slot 2). Kept in named registers (no dynamically indexed local arrays)
+  bool hasA = false, hasB = false; D3 dirA = d3(0, 0, 0), wA = dirA, dirB = dirA, wB = dirA, orgC = dirA; double ktA0 = 1, ktA1 = 1, ktB0 = 1, ktB1 = 1;
+  uint32_t cka = 0, ckb = 0, ckc = 0, cstream = 0; int32_t cgen = 0;
   unsigned long long cPrimary = 0, cRefl = 0, cRefr = 0;
   if (i < n) {
     const RayRec r = rays[i]; const Hit h = hits[i];
@@ -156,13 +158,9 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene S,
         s.rawDir[0] = h.rawDir.x; s.rawDir[1] = h.rawDir.y; s.rawDir[2] = h.rawDir.z; s.tex[0] = tex.x; s.tex[1] = tex.y; s.tex[2] = tex.z;
         // secondary rays (leave room for the shadow generation: gen < numRays - 2)
         if ((r.gen < S.g.numRays - 2) && (sh.flags & SF_HAS_CAUSTIC)) {
+          orgC = fwd; cka = r.ka; ckb = r.kb; ckc = r.kc; cstream = r.stream; cgen = r.gen + 1;
           auto child = [&](int slot, D3 dir, D3 w, double kt0, double kt1) {
-            RayRec& c = ch[nChild]; NodeRec& nn = cn[nChild]; ++nChild;
-            D3 dn = norm3(dir);
-            c.o[0] = fwd.x; c.o[1] = fwd.y; c.o[2] = fwd.z; c.d[0] = dn.x; c.d[1] = dn.y; c.d[2] = dn.z; c.kt0 = kt0; c.kt1 = kt1;
-            c.ka = r.ka; c.kb = r.kb; c.kc = r.kc * 2 + (slot == 1 ? 1 : 0); c.stream = r.stream; c.gen = r.gen + 1; c.valid = 1; c.pad[0] = c.pad[1] = 0;
-            nn.parent = (int32_t)i; nn.slot = slot; nn.pad[0] = nn.pad[1] = 0; nn.w[0] = w.x; nn.w[1] = w.y; nn.w[2] = w.z;
-            for (int k = 0; k < 3; ++k) { nn.local[k] = 0; nn.cA[k] = 0; nn.cB[k] = 0; }
+            if (slot == 1) { hasA = true; dirA = norm3(dir); wA = w; ktA0 = kt0; ktA1 = kt1; } else { hasB = true; dirB = norm3(dir); wB = w; ktB0 = kt0; ktB1 = kt1; }
           };
           D3 perm = d3(sh.perm[0], sh.perm[1], sh.perm[2]);
           bool trans = simple ? (sh.KTrans > 0) : ((sh.KTrans > 0) || (sh.currPerm > 0.0));
@@ -186,14 +184,26 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene S,
   }
   // warp-aggregated compaction of the children into the next level's queue
   unsigned lane = threadIdx.x & 31;
+  const int nChild = (hasA ? 1 : 0) + (hasB ? 1 : 0);
   int incl = nChild;
   for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += v; }
   int total = __shfl_sync(0xffffffffu, incl, 31);
   unsigned long long base = 0;
   if (total > 0) { if (lane == 31) base = atomicAdd(&ctr->nextCount, (unsigned long long)total); base = __shfl_sync(0xffffffffu, base, 31); }
   long long at = (long long)base + (incl - nChild);
-  for (int k = 0; k < nChild; ++k) if (at + k < nextCap) { nextRays[at + k] = ch[k]; nextNodes[at + k] = cn[k]; }
-  warpAdd(&ctr->primary, cPrimary); warpAdd(&ctr->reflect, cRefl); warpAdd(&ctr->refract, cRefr);
+  auto emit = [&](long long pos, int slot, D3 dn, D3 w, double kt0, double kt1) {
+    if (pos >= nextCap) return;
+    RayRec c; c.o[0] = orgC.x; c.o[1] = orgC.y; c.o[2] = orgC.z; c.d[0] = dn.x; c.d[1] = dn.y; c.d[2] = dn.z; c.kt0 = kt0; c.kt1 = kt1;
+    c.ka = cka; c.kb = ckb; c.kc = ckc * 2 + (slot == 1 ? 1 : 0); c.stream = cstream; c.gen = cgen; c.valid = 1; c.pad[0] = c.pad[1] = 0;
+    NodeRec nn; nn.parent = (int32_t)i; nn.slot = slot; nn.pad[0] = nn.pad[1] = 0; nn.w[0] = w.x; nn.w[1] = w.y; nn.w[2] = w.z;
+    for (int k = 0; k < 3; ++k) { nn.local[k] = 0; nn.cA[k] = 0; nn.cB[k] = 0; }
+    nextRays[pos] = c; nextNodes[pos] = nn;
+  };
+  if (hasA) emit(at, 1, dirA, wA, ktA0, ktA1);
+  if (hasB) emit(at + (hasA ? 1 : 0), 2, dirB, wB, ktB0, ktB1);
+  // 0/1 flags: one ballot + popc per counter instead of a 64-bit shuffle tree
+  { const unsigned bp = __ballot_sync(0xffffffffu, cPrimary != 0), bl = __ballot_sync(0xffffffffu, cRefl != 0), br = __ballot_sync(0xffffffffu, cRefr != 0);
+    if (lane == 0) { if (bp) atomicAdd(&ctr->primary, (unsigned long long)__popc(bp)); if (bl) atomicAdd(&ctr->reflect, (unsigned long long)__popc(bl)); if (br) atomicAdd(&ctr->refract, (unsigned long long)__popc(br)); } }
 }
 
 // Light pass: literal calcShadowColor, one thread per shaded hit, lights in list order, shadow rays traced in-thread.
@@ -309,15 +319,28 @@ template <class T> struct DBuf {
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
-template <class T> static const T* uploadVec(const std::vector<T>& v, std::vector<void*>& owned, cudaStream_t st) {
-  T* d = nullptr; size_t n = v.size() ? v.size() : 1;
-  CK(cudaMalloc(&d, n * sizeof(T))); owned.push_back(d);
-  if (v.size()) CK(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
-  return d;
-}
+// Scene arrays live in ONE device arena fed from ONE pinned host staging buffer (grow-only): a re-upload is a host memcpy per array plus a
+// single H2D DMA -- no cudaMalloc / cudaFree on the per-frame path.
+struct SceneArena {
+  char* dev = nullptr; char* host = nullptr; size_t cap = 0, used = 0;
+  void reserve(size_t bytes, cudaStream_t st) {
+    if (bytes <= cap) return;
+    CK(cudaStreamSynchronize(st)); if (dev) cudaFree(dev); if (host) cudaFreeHost(host);
+    cap = bytes + bytes / 4 + (1 << 20); CK(cudaMalloc(&dev, cap)); CK(cudaMallocHost(&host, cap));
+  }
+  void begin() { used = 0; }
+  template <class T> const T* put(const std::vector<T>& v) {
+    used = (used + 255) & ~(size_t)255; const size_t at = used; const size_t n = v.size() * sizeof(T);
+    if (n) std::memcpy(host + at, v.data(), n);
+    used += n ? n : sizeof(T); return reinterpret_cast<const T*>(dev + at);
+  }
+  template <class T> static size_t need(const std::vector<T>& v) { return ((v.size() ? v.size() : 1) * sizeof(T) + 255) & ~(size_t)255; }
+  void flush(cudaStream_t st) { if (used) CK(cudaMemcpyAsync(dev, host, used, cudaMemcpyHostToDevice, st)); }
+  void release() { if (dev) cudaFree(dev); if (host) cudaFreeHost(host); dev = host = nullptr; cap = used = 0; }
+};
 
 struct Renderer::Impl {
-  DScene ds; std::vector<void*> owned;
+  DScene ds; SceneArena arena; DBuf<FNode> lbvhNodeBuf; DBuf<FTri> lbvhTriBuf; LbvhScratch lbvhScratch;
   DBuf<RayRec> rays[2]; DBuf<Hit> hits; DBuf<Hit> hits0; DBuf<SurfRec> surf; DBuf<NodeRec> nodes; Counters* ctr = nullptr; Counters* ctrHost = nullptr;
   DBuf<int32_t> oArgb, oPrim, oInst; DBuf<double> oRgb, oT;
   cudaEvent_t ev[8];
@@ -340,7 +363,7 @@ Renderer::Renderer(int device) : impl_(new Impl), device_(device) {
 }
 Renderer::~Renderer() {
   cudaSetDevice(device_);
-  for (void* p : impl_->owned) cudaFree(p);
+  impl_->arena.release(); impl_->lbvhNodeBuf.release(); impl_->lbvhTriBuf.release(); impl_->lbvhScratch.release();
   impl_->rays[0].release(); impl_->rays[1].release(); impl_->hits.release(); impl_->hits0.release(); impl_->surf.release(); impl_->nodes.release();
   impl_->oArgb.release(); impl_->oPrim.release(); impl_->oInst.release(); impl_->oRgb.release(); impl_->oT.release();
   impl_->photons.release();
@@ -352,7 +375,6 @@ Renderer::~Renderer() {
 void Renderer::upload(const HostScene& hs) {
   CK(cudaSetDevice(device_)); cudaStream_t st = (cudaStream_t)stream_;
   CK(cudaStreamSynchronize(st));
-  for (void* p : impl_->owned) cudaFree(p); impl_->owned.clear();
   // device-side nesting limits (see dev_isect.cuh): accel children are primitives or instances; an instanced accel holds primitives
   for (const FInstance& in : hs.instances) if (in.baseKind == OK_LIST || in.baseKind == OK_BVH) {
     auto checkList = [&](const FList& L) { for (int i = 0; i < L.childCount; ++i) { const FObjRef& c = hs.children[L.childStart + i];
@@ -360,35 +382,38 @@ void Renderer::upload(const HostScene& hs) {
     if (in.baseKind == OK_LIST) checkList(hs.lists[in.baseIdx]);
     else { std::vector<int32_t> st2{hs.bvhs[in.baseIdx].root}; while (!st2.empty()) { int32_t r = st2.back(); st2.pop_back(); if (r < 0) checkList(hs.lists[~r]); else { st2.push_back(hs.nodes[r].left); st2.push_back(hs.nodes[r].right); } } }
   }
-  DScene& d = impl_->ds; auto& ow = impl_->owned;
-  d.xforms = uploadVec(hs.xforms, ow, st); d.prims = uploadVec(hs.prims, ow, st); d.pdata = uploadVec(hs.pdata, ow, st); d.top = uploadVec(hs.top, ow, st);
-  d.children = uploadVec(hs.children, ow, st); d.instances = uploadVec(hs.instances, ow, st); d.lists = uploadVec(hs.lists, ow, st);
-  d.nodes = uploadVec(hs.nodes, ow, st); d.tris = uploadVec(hs.tris, ow, st); d.fnodes = d.nodes; d.accelMode = traceMode_ & 3; d.padA = 0;
-  // DRT_ACCEL_LBVH: rebuild every qualifying pure-triangle BVH on the GPU (see lbvh.cuh). The reference-topology nodes stay resident
-  // (instance-level trees, BVHs that do not qualify, and rays whose units forbid reordering still use them).
-  std::vector<FBvh> bv = hs.bvhs; impl_->lbvhMs = 0; impl_->lbvhTris = 0; impl_->lbvhNodes = 0;
-  if (d.accelMode == 2) {
-    size_t extra = 0; for (const FBvh& B : bv) if (B.fast && B.triXform == B.xform && B.triCount > 4) extra += (size_t)((B.triCount + 3) / 4 - 1);
-    if (extra) {
-      const size_t n0 = hs.nodes.size(); FNode* ln = nullptr; FTri* lt = nullptr;
-      CK(cudaMalloc(&ln, (n0 + extra) * sizeof(FNode))); ow.push_back(ln); CK(cudaMalloc(&lt, (hs.tris.size() ? hs.tris.size() : 1) * sizeof(FTri))); ow.push_back(lt);
-      if (n0) CK(cudaMemcpyAsync(ln, d.nodes, n0 * sizeof(FNode), cudaMemcpyDeviceToDevice, st));
-      CK(cudaMemcpyAsync(lt, d.tris, hs.tris.size() * sizeof(FTri), cudaMemcpyDeviceToDevice, st));
-      cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventRecord(e0, st));
-      size_t at = n0; LbvhScratch sc;
-      for (FBvh& B : bv) if (B.fast && B.triXform == B.xform && B.triCount > 4) {
-        const int wrote = lbvhBuild(lt, B.triStart, B.triCount, B.bmin, B.bmax, ln + at, (int)at, sc, st);
-        if (wrote > 0) { B.fastRoot = (int32_t)at; at += (size_t)wrote; impl_->lbvhTris += B.triCount; impl_->lbvhNodes += wrote; }
-      }
-      CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError()); CK(cudaEventElapsedTime(&impl_->lbvhMs, e0, e1));
-      cudaEventDestroy(e0); cudaEventDestroy(e1); sc.release();
-      d.fnodes = ln; d.tris = lt;
+  DScene& d = impl_->ds; SceneArena& A = impl_->arena;
+  std::vector<FBvh> bv = hs.bvhs;
+  d.accelMode = traceMode_ & 3; d.padA = 0;
+  // DRT_ACCEL_LBVH: every qualifying pure-triangle BVH is rebuilt on the GPU (lbvh.cuh) after the copy. Node slots: the reference nodes
+  // first (instance-level trees, BVHs that do not qualify, rays whose units forbid reordering keep using them), LBVH nodes appended.
+  size_t extra = 0;
+  if (d.accelMode == 2) for (FBvh& B : bv) if (B.fast && B.triXform == B.xform && B.triCount > 4) { B.fastRoot = (int32_t)(hs.nodes.size() + extra); extra += (size_t)((B.triCount + 3) / 4 - 1); }
+  A.reserve(SceneArena::need(hs.xforms) + SceneArena::need(hs.prims) + SceneArena::need(hs.pdata) + SceneArena::need(hs.top) + SceneArena::need(hs.children) + SceneArena::need(hs.instances) +
+            SceneArena::need(hs.lists) + SceneArena::need(hs.nodes) + SceneArena::need(hs.tris) + SceneArena::need(bv) + SceneArena::need(hs.lights) + SceneArena::need(hs.shaders) +
+            SceneArena::need(hs.textures) + SceneArena::need(hs.texColors) + SceneArena::need(hs.images) + SceneArena::need(hs.texels) + 4096, st);
+  A.begin();
+  d.xforms = A.put(hs.xforms); d.prims = A.put(hs.prims); d.pdata = A.put(hs.pdata); d.top = A.put(hs.top); d.children = A.put(hs.children); d.instances = A.put(hs.instances);
+  d.lists = A.put(hs.lists); d.nodes = A.put(hs.nodes); d.tris = A.put(hs.tris); d.bvhs = A.put(bv); d.lights = A.put(hs.lights); d.shaders = A.put(hs.shaders);
+  d.textures = A.put(hs.textures); d.texColors = A.put(hs.texColors); d.images = A.put(hs.images); d.texels = A.put(hs.texels);
+  A.flush(st);
+  d.fnodes = d.nodes; impl_->lbvhMs = 0; impl_->lbvhTris = 0; impl_->lbvhNodes = 0;
+  if (extra) {
+    const size_t n0 = hs.nodes.size();
+    impl_->lbvhNodeBuf.ensure(n0 + extra, st); impl_->lbvhTriBuf.ensure(hs.tris.size(), st);
+    FNode* ln = impl_->lbvhNodeBuf.p; FTri* lt = impl_->lbvhTriBuf.p;
+    if (n0) CK(cudaMemcpyAsync(ln, d.nodes, n0 * sizeof(FNode), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(lt, d.tris, hs.tris.size() * sizeof(FTri), cudaMemcpyDeviceToDevice, st));
+    CK(cudaEventRecord(impl_->ev[6], st));
+    for (const FBvh& B : bv) if (B.fast && B.fastRoot != B.root) {
+      const int wrote = lbvhBuild(lt, B.triStart, B.triCount, B.bmin, B.bmax, ln + B.fastRoot, B.fastRoot, impl_->lbvhScratch, st);
+      if (wrote != (B.triCount + 3) / 4 - 1) throw std::runtime_error("LBVH node count mismatch");
+      impl_->lbvhTris += B.triCount; impl_->lbvhNodes += wrote;
     }
+    CK(cudaEventRecord(impl_->ev[7], st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError()); CK(cudaEventElapsedTime(&impl_->lbvhMs, impl_->ev[6], impl_->ev[7]));
+    d.fnodes = ln; d.tris = lt;
   }
-  d.bvhs = uploadVec(bv, ow, st); CK(cudaStreamSynchronize(st));      // bv is a local: finish the copy before it goes away
-  d.lights = uploadVec(hs.lights, ow, st); d.shaders = uploadVec(hs.shaders, ow, st); d.textures = uploadVec(hs.textures, ow, st);
-  d.texColors = uploadVec(hs.texColors, ow, st); d.images = uploadVec(hs.images, ow, st); d.texels = uploadVec(hs.texels, ow, st);
-  impl_->sceneBytes = hs.xforms.size() * sizeof(FXform) + hs.prims.size() * sizeof(FPrim) + hs.pdata.size() * 8 + hs.children.size() * sizeof(FObjRef) + hs.nodes.size() * sizeof(FNode) + hs.tris.size() * sizeof(FTri) + hs.lists.size() * sizeof(FList) + hs.texels.size() * 4;
+  impl_->sceneBytes = A.used;                              // bytes copied host -> device by this upload
   d.g = hs.g; d.g.pad0 = 0;
   for (const FPrim& p : hs.prims) if (p.type == PT_MOVSPHERE) d.g.pad0 = 1;
   d.numPhotons = 0; d.phPos = nullptr; d.phPwr = nullptr; d.cellStart = nullptr; d.cellEnd = nullptr;
