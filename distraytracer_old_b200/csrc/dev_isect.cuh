@@ -269,6 +269,14 @@ __device__ __forceinline__ bool boxTestStd(const double* mn, const double* mx, c
 // deeper levels (only unbalanced LBVHs get there) in a small local array.  Keeping the stack out of local memory matters: with ~110 k
 // resident threads a per-thread local frame of a few KB is larger than L2 and turns every push/pop into DRAM traffic (profiles/r1b).
 // entry.x = child reference (>= 0 inner node, < 0: ~tri-leaf code), entry.y = bits of the box-entry t rounded DOWN to float.
+#ifndef DRT_LEAN
+#define DRT_LEAN 1
+#endif
+// The traversal bodies are force-inlined: as __noinline__ functions (one shared copy) they ran at the same speed but one build computed wrong
+// closest hits in unrelated, never-executed-together paths of the same kernel (found by tools/dbg_modes2.py, not explained) -- see DESIGN.md.
+#ifndef DRT_LEAN_INLINE
+#define DRT_LEAN_INLINE __forceinline__
+#endif
 #define DRT_TB 128              // threads per block of every kernel that traces
 #ifndef DRT_SSTACK
 #define DRT_SSTACK 0            // levels kept in shared memory; measured on B200 (profiles/r1_tuning.md): shared levels cost more L1 capacity than they save
@@ -298,11 +306,15 @@ struct FStack {
 __device__ __forceinline__ int32_t childRef(int32_t link, int32_t triCode) { return link >= 0 ? link : ~triCode; }
 
 // Closest hit inside one fast BVH (root box already accepted by the caller). `trans` is the ray the boxes are tested with,
-// `r` the ray the triangles are tested with (see SURVEY Q7 for why they can differ).  Result: the minimum-t hit over every leaf
-// whose chain of boxes is accepted -- the set the reference's left-first recursion searches; equal-t candidates resolve to the
-// lower reference rank, i.e. the reference's visiting order.
-template <bool STD_BOX>
-__device__ __forceinline__ bool fastClosest(const DScene& S, const FBvh& B, const Ray& trans, const Ray& r, D3 rawDir, Hit& out, TraceCounters* tc) {
+// `r` the ray the triangles are tested with (see SURVEY Q7 for why they can differ; ONE_RAY: they are bitwise the same ray, which is
+// the case for every mesh that is not reached through an instance -- half the live registers).  Result: the minimum-t hit over every
+// leaf whose chain of boxes is accepted -- the set the reference's left-first recursion searches; equal-t candidates resolve to the
+// lower reference rank, i.e. the reference's visiting order.  stdBox: LBVH mode's conventional slab test.
+template <bool ONE_RAY>
+__device__ DRT_LEAN_INLINE bool fastClosest(const DScene& S, const FBvh& B, const Ray& transIn, const Ray& rIn, D3 rawDir, Hit& out, TraceCounters* tc) {
+  Ray trans; trans.o = transIn.o; trans.a = transIn.a; trans.d = transIn.a; trans.norm = false;
+  Ray r; if (ONE_RAY) r = trans; else { r.o = rIn.o; r.d = rIn.d; r.a = rIn.d; r.norm = false; }
+  const bool stdBox = S.accelMode == 2;
   const D3 inv = rayInv(trans);
   FStack stk;
   double bestT = DRT_DMAX; int bestTri = -1, bestRank = 0x7fffffff, bestSt = 0;
@@ -311,8 +323,9 @@ __device__ __forceinline__ bool fastClosest(const DScene& S, const FBvh& B, cons
     if (ref >= 0) {
       double bx[12]; int32_t left, right, triL, triR; ldNode(S.fnodes + ref, bx, left, right, triL, triR);
       double teL, teR; if (tc) tc->box += 2;
-      bool hl = STD_BOX ? boxTestStd(bx, bx + 3, trans, inv, teL) : boxAcceptLB(bx, bx + 3, trans, inv, teL);
-      bool hr = STD_BOX ? boxTestStd(bx + 6, bx + 9, trans, inv, teR) : boxAcceptLB(bx + 6, bx + 9, trans, inv, teR);
+      bool hl, hr;
+      if (stdBox) { hl = boxTestStd(bx, bx + 3, trans, inv, teL); hr = boxTestStd(bx + 6, bx + 9, trans, inv, teR); }
+      else { hl = boxAcceptLB(bx, bx + 3, trans, inv, teL); hr = boxAcceptLB(bx + 6, bx + 9, trans, inv, teR); }
       hl = hl && teL < bestT; hr = hr && teR < bestT;
       const int32_t cl = childRef(left, triL), cr = childRef(right, triR);
       if (hl && hr) {
@@ -343,8 +356,11 @@ __device__ __forceinline__ bool fastClosest(const DScene& S, const FBvh& B, cons
   }
 }
 // Any hit inside one fast BVH: (dist - t) > eps for a triangle, every box on the way accepted with (dist - entry) > eps
-template <bool STD_BOX>
-__device__ __forceinline__ bool fastShadow(const DScene& S, const FBvh& B, const Ray& trans, const Ray& r, double dist, TraceCounters* tc) {
+template <bool ONE_RAY>
+__device__ DRT_LEAN_INLINE bool fastShadow(const DScene& S, const FBvh& B, const Ray& transIn, const Ray& rIn, double dist, TraceCounters* tc) {
+  Ray trans; trans.o = transIn.o; trans.a = transIn.a; trans.d = transIn.a; trans.norm = false;
+  Ray r; if (ONE_RAY) r = trans; else { r.o = rIn.o; r.d = rIn.d; r.a = rIn.d; r.norm = false; }
+  const bool stdBox = S.accelMode == 2;
   const D3 inv = rayInv(trans);
   FStack stk;
   int32_t ref = B.fastRoot;
@@ -352,8 +368,9 @@ __device__ __forceinline__ bool fastShadow(const DScene& S, const FBvh& B, const
     if (ref >= 0) {
       double bx[12]; int32_t left, right, triL, triR; ldNode(S.fnodes + ref, bx, left, right, triL, triR);
       double teL, teR; if (tc) tc->box += 2;
-      const bool hl = STD_BOX ? (boxTestStd(bx, bx + 3, trans, inv, teL) && (dist - teL) > DRT_EPS) : boxAcceptShadow(bx, bx + 3, trans, inv, dist);
-      const bool hr = STD_BOX ? (boxTestStd(bx + 6, bx + 9, trans, inv, teR) && (dist - teR) > DRT_EPS) : boxAcceptShadow(bx + 6, bx + 9, trans, inv, dist);
+      bool hl, hr;
+      if (stdBox) { hl = boxTestStd(bx, bx + 3, trans, inv, teL) && (dist - teL) > DRT_EPS; hr = boxTestStd(bx + 6, bx + 9, trans, inv, teR) && (dist - teR) > DRT_EPS; }
+      else { hl = boxAcceptShadow(bx, bx + 3, trans, inv, dist); hr = boxAcceptShadow(bx + 6, bx + 9, trans, inv, dist); }
       const int32_t cl = childRef(left, triL), cr = childRef(right, triR);
       if (hl && hr) { stk.push(cr, 0.f); ref = cl; continue; }
       if (hl) { ref = cl; continue; }
@@ -370,6 +387,148 @@ __device__ __forceinline__ bool fastShadow(const DScene& S, const FBvh& B, const
     ref = (int32_t)stk.pop().x;
   }
 }
+// ---- lean descent for "regular" rays (every direction component finite, non-zero and of sane magnitude: all but axis-parallel rays)
+// The per-axis ordering the reference derives from `v1 < v2` is the sign of the direction component (node boxes of fast BVHs have
+// min <= max, checked by the host), so the near/far slab planes are picked per RAY, and each box costs 6 subtractions, 6 products, two
+// 3-way max/min and the margin check of boxQuick().  Anything inside the margin goes to the exact test, out of line.
+struct LeanRay { double ox, oy, oz, ix, iy, iz; bool px, py, pz; };
+__device__ __noinline__ bool boxExactLB(const double* __restrict__ box6, double ox, double oy, double oz, double ax, double ay, double az, double& te) {
+  Ray r; r.o = d3(ox, oy, oz); r.a = d3(ax, ay, az); r.d = r.a; r.norm = false; int face;
+  double b[6]; for (int i = 0; i < 6; ++i) b[i] = __ldg(box6 + i);
+  return boxTest(b, b + 3, r, te, face);
+}
+// 1 accepted / 0 rejected / -1 undecided; nearOut = entry t to ~3e-16 relative
+__device__ __forceinline__ int leanBox(double mnx, double mny, double mnz, double mxx, double mxy, double mxz, const LeanRay& R, double& nearOut) {
+  const double nx = ((R.px ? mnx : mxx) - R.ox) * R.ix, fx = ((R.px ? mxx : mnx) - R.ox) * R.ix;
+  const double ny = ((R.py ? mny : mxy) - R.oy) * R.iy, fy = ((R.py ? mxy : mny) - R.oy) * R.iy;
+  const double nz = ((R.pz ? mnz : mxz) - R.oz) * R.iz, fz = ((R.pz ? mxz : mnz) - R.oz) * R.iz;
+  double near_ = nx > ny ? nx : ny; near_ = nz > near_ ? nz : near_;
+  double far_ = fx < fy ? fx : fy; far_ = fz < far_ ? fz : far_;
+  nearOut = near_;
+  if (!(fabs(near_) > 1e-290)) return -1;
+  const double tol = 1e-14 * (fabs(far_) + fabs(near_)), gap = far_ - near_;
+  if (gap > tol) return near_ > 0 ? 1 : 0;
+  return (-gap > tol) ? 0 : -1;
+}
+__device__ __forceinline__ bool regularDir(D3 a) {
+  const double x = fabs(a.x), y = fabs(a.y), z = fabs(a.z);
+  return x > 1e-100 && x < 1e100 && y > 1e-100 && y < 1e100 && z > 1e-100 && z < 1e100;
+}
+// triangle test of triTestPacked with one shortcut that cannot change the outcome: a plane hit farther than the best hit so far is
+// dropped before the inside test (the reference would compute it and then discard it in `t < closest`)
+__device__ __forceinline__ bool leanTri(const FTri* __restrict__ T, double ox, double oy, double oz, double dx, double dy, double dz, double bestT, double& tOut, int& stOut, int32_t& rank) {
+  const double2* __restrict__ q = reinterpret_cast<const double2*>(T);
+  const double2 q4 = __ldg(q + 4), q5 = __ldg(q + 5), q6 = __ldg(q + 6);                    // (v8, N.x) (N.y, N.z) (D, Drev)
+  double Nx = q4.y, Ny = q5.x, Nz = q5.y, D = q6.x;
+  double planeRes = ((Nx * dx) + (Ny * dy)) + (Nz * dz);
+  if (!(fabs(planeRes) > 0)) return false;
+  int st = 0;
+  if (planeRes > 0) { st = 1; Nx = -Nx; Ny = -Ny; Nz = -Nz; D = q6.y; planeRes = -planeRes; }
+  const double t = -((((Nx * ox) + (Ny * oy)) + (Nz * oz)) + D) / planeRes;
+  if (!(t > DRT_EPS) || t > bestT) return false;
+  const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);     // (v0 v1) (v2 v3) (v4 v5) (v6 v7)
+  const double px = (dx * t) + ox, py = (dy * t) + oy, pz = (dz * t) + oz;
+  const double ax_ = q0.x, ay_ = q0.y, az_ = q1.x, bx_ = q1.y, by_ = q2.x, bz_ = q2.y, cx_ = q3.x, cy_ = q3.y, cz_ = q4.x;
+  const double V0x = st ? cx_ : ax_, V0y = st ? cy_ : ay_, V0z = st ? cz_ : az_, V2x = st ? ax_ : cx_, V2y = st ? ay_ : cy_, V2z = st ? az_ : cz_;
+  { const double ix = px - V0x, iy = py - V0y, iz = pz - V0z, ex = V0x - V2x, ey = V0y - V2y, ez = V0z - V2z;
+    const double cxx = (iy * ez) - (iz * ey), cyy = (iz * ex) - (ix * ez), czz = (ix * ey) - (iy * ex);
+    if ((((cxx * Nx) + (cyy * Ny)) + (czz * Nz)) < -DRT_EPS) return false; }
+  { const double ix = px - bx_, iy = py - by_, iz = pz - bz_, ex = bx_ - V0x, ey = by_ - V0y, ez = bz_ - V0z;
+    const double cxx = (iy * ez) - (iz * ey), cyy = (iz * ex) - (ix * ez), czz = (ix * ey) - (iy * ex);
+    if ((((cxx * Nx) + (cyy * Ny)) + (czz * Nz)) < -DRT_EPS) return false; }
+  { const double ix = px - V2x, iy = py - V2y, iz = pz - V2z, ex = V2x - bx_, ey = V2y - by_, ez = V2z - bz_;
+    const double cxx = (iy * ez) - (iz * ey), cyy = (iz * ex) - (ix * ez), czz = (ix * ey) - (iy * ex);
+    if ((((cxx * Nx) + (cyy * Ny)) + (czz * Nz)) < -DRT_EPS) return false; }
+  rank = __ldg(reinterpret_cast<const int32_t*>(T) + 29);
+  tOut = t; stOut = st; return true;
+}
+template <bool ONE_RAY>
+__device__ DRT_LEAN_INLINE bool leanClosest(const DScene& S, const FBvh& B, const D3 bo, const D3 ba, const D3 to, const D3 td, const D3 rawDir, Hit& out, TraceCounters* tc) {
+  LeanRay R; R.ox = bo.x; R.oy = bo.y; R.oz = bo.z;
+  const double ax = ba.x, ay = ba.y, az = ba.z;
+  R.ix = 1.0 / ax; R.iy = 1.0 / ay; R.iz = 1.0 / az; R.px = ax > 0; R.py = ay > 0; R.pz = az > 0;
+  const double tox = ONE_RAY ? R.ox : to.x, toy = ONE_RAY ? R.oy : to.y, toz = ONE_RAY ? R.oz : to.z;
+  const double tdx = ONE_RAY ? ax : td.x, tdy = ONE_RAY ? ay : td.y, tdz = ONE_RAY ? az : td.z;
+  FStack stk;
+  double bestT = DRT_DMAX; int bestTri = -1, bestRank = 0x7fffffff, bestSt = 0;
+  int32_t ref = B.fastRoot;
+  while (true) {
+    if (ref >= 0) {
+      const double2* q = reinterpret_cast<const double2*>(S.fnodes + ref);
+      const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5);
+      const int4 lk = __ldg(reinterpret_cast<const int4*>(q) + 6);
+      if (tc) tc->box += 2;
+      double teL, teR;
+      const int ql = leanBox(q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, R, teL), qr = leanBox(q3.x, q3.y, q4.x, q4.y, q5.x, q5.y, R, teR);
+      bool hl = ql > 0, hr = qr > 0;
+      if (ql >= 0) teL *= 0.999999999999999; else hl = boxExactLB(reinterpret_cast<const double*>(q), R.ox, R.oy, R.oz, ax, ay, az, teL);
+      if (qr >= 0) teR *= 0.999999999999999; else hr = boxExactLB(reinterpret_cast<const double*>(q) + 6, R.ox, R.oy, R.oz, ax, ay, az, teR);
+      hl = hl && teL < bestT; hr = hr && teR < bestT;
+      const int32_t cl = childRef(lk.x, lk.z), cr = childRef(lk.y, lk.w);
+      if (hl && hr) {
+        const bool rightFirst = teR < teL;
+        stk.push(rightFirst ? cl : cr, __double2float_rd(rightFirst ? teL : teR));
+        ref = rightFirst ? cr : cl; continue;
+      }
+      if (hl) { ref = cl; continue; }
+      if (hr) { ref = cr; continue; }
+    } else {
+      const int code = ~ref, cnt = code & 7, first = code >> 3;
+      for (int i = 0; i < cnt; ++i) {
+        double t; int st; int32_t rank; if (tc) ++tc->prim;
+        if (leanTri(S.tris + first + i, tox, toy, toz, tdx, tdy, tdz, bestT, t, st, rank) && (t < bestT || rank < bestRank)) { bestT = t; bestTri = first + i; bestRank = rank; bestSt = st; }
+      }
+    }
+    while (true) {
+      if (stk.sp == 0) {
+        if (bestTri < 0) return false;
+        out.t = bestT; out.prim = S.tris[bestTri].prim; out.arg0 = 0; out.arg1 = 0; out.state = bestSt; out.hitXform = B.triHitXform; out.shaderOverride = -1; out.inst = -1;
+        out.loc = d3((tdx * bestT) + tox, (tdy * bestT) + toy, (tdz * bestT) + toz); out.rawDir = rawDir; return true;
+      }
+      const uint2 e = stk.pop();
+      if ((double)__uint_as_float(e.y) < bestT) { ref = (int32_t)e.x; break; }
+    }
+  }
+}
+template <bool ONE_RAY>
+__device__ DRT_LEAN_INLINE bool leanShadow(const DScene& S, const FBvh& B, const D3 bo, const D3 ba, const D3 to, const D3 td, double dist, TraceCounters* tc) {
+  LeanRay R; R.ox = bo.x; R.oy = bo.y; R.oz = bo.z;
+  const double ax = ba.x, ay = ba.y, az = ba.z;
+  R.ix = 1.0 / ax; R.iy = 1.0 / ay; R.iz = 1.0 / az; R.px = ax > 0; R.py = ay > 0; R.pz = az > 0;
+  const double tox = ONE_RAY ? R.ox : to.x, toy = ONE_RAY ? R.oy : to.y, toz = ONE_RAY ? R.oz : to.z;
+  const double tdx = ONE_RAY ? ax : td.x, tdy = ONE_RAY ? ay : td.y, tdz = ONE_RAY ? az : td.z;
+  FStack stk;
+  int32_t ref = B.fastRoot;
+  auto accept = [&](int q, double te, const double* box6) {       // (dist - entry) > eps, with the exact entry t only when it is too close to call
+    if (q == 0) return false;
+    if (q > 0) { const double diff = dist - te, m = 1e-13 * (fabs(dist) + fabs(te)); if (diff > DRT_EPS + m) return true; if (diff < DRT_EPS - m) return false; }
+    double tx; return boxExactLB(box6, R.ox, R.oy, R.oz, ax, ay, az, tx) && (dist - tx) > DRT_EPS;
+  };
+  while (true) {
+    if (ref >= 0) {
+      const double2* q = reinterpret_cast<const double2*>(S.fnodes + ref);
+      const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5);
+      const int4 lk = __ldg(reinterpret_cast<const int4*>(q) + 6);
+      if (tc) tc->box += 2;
+      double teL, teR;
+      const int ql = leanBox(q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, R, teL), qr = leanBox(q3.x, q3.y, q4.x, q4.y, q5.x, q5.y, R, teR);
+      const bool hl = accept(ql, teL, reinterpret_cast<const double*>(q)), hr = accept(qr, teR, reinterpret_cast<const double*>(q) + 6);
+      const int32_t cl = childRef(lk.x, lk.z), cr = childRef(lk.y, lk.w);
+      if (hl && hr) { stk.push(cr, 0.f); ref = cl; continue; }
+      if (hl) { ref = cl; continue; }
+      if (hr) { ref = cr; continue; }
+    } else {
+      const int code = ~ref, cnt = code & 7, first = code >> 3;
+      for (int i = 0; i < cnt; ++i) {
+        double t; int st; int32_t rank; if (tc) ++tc->prim;
+        if (leanTri(S.tris + first + i, tox, toy, toz, tdx, tdy, tdz, DRT_DMAX, t, st, rank) && (dist - t) > DRT_EPS) return true;
+      }
+    }
+    if (stk.sp == 0) return false;
+    ref = (int32_t)stk.pop().x;
+  }
+}
+__device__ __forceinline__ bool sameRay(const Ray& trans, const Ray& r) { return trans.o.x == r.o.x && trans.o.y == r.o.y && trans.o.z == r.o.z && trans.a.x == r.d.x && trans.a.y == r.d.y && trans.a.z == r.d.z; }
 // may this BVH be searched out of the reference's order for this pair of rays?  (through an instance the triangles see a
 // re-normalised direction, so hit t and box-entry t are in different units; pruning stays conservative only if the local direction
 // was at least unit length)
@@ -444,7 +603,11 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
     const double len2 = _ray.norm ? 1.0 : dot3(_ray.d, _ray.d);
     if (fastUsable(S, B, len2)) {
       const Ray r = xfRay(_ray, S.xforms[B.triXform].inv);          // what every leaf child of this mesh would be tested with
-      return (S.accelMode == 2) ? fastClosest<true>(S, B, trans, r, _ray.d, out, tc) : fastClosest<false>(S, B, trans, r, _ray.d, out, tc);
+      const bool one = sameRay(trans, r);
+#if DRT_LEAN
+      if (S.accelMode == 1 && regularDir(trans.a)) return one ? leanClosest<true>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc) : leanClosest<false>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc);
+#endif
+      return one ? fastClosest<true>(S, B, trans, r, _ray.d, out, tc) : fastClosest<false>(S, B, trans, r, _ray.d, out, tc);
     }
   }
   const D3 inv = rayInv(trans);
@@ -550,7 +713,11 @@ __device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const
   const FBvh& B = S.bvhs[idx];
   if (S.accelMode != 0 && B.fast != 0) {                              // any-hit does not depend on the visiting order
     const Ray r = xfRay(_ray, S.xforms[B.triXform].inv);
-    return (S.accelMode == 2) ? fastShadow<true>(S, B, trans, r, dist, tc) : fastShadow<false>(S, B, trans, r, dist, tc);
+    const bool one = sameRay(trans, r);
+#if DRT_LEAN
+    if (S.accelMode == 1 && regularDir(trans.a)) return one ? leanShadow<true>(S, B, trans.o, trans.a, r.o, r.d, dist, tc) : leanShadow<false>(S, B, trans.o, trans.a, r.o, r.d, dist, tc);
+#endif
+    return one ? fastShadow<true>(S, B, trans, r, dist, tc) : fastShadow<false>(S, B, trans, r, dist, tc);
   }
   int32_t stack[DRT_STACK]; int sp = 0; int32_t node = B.root;
   double te;

@@ -353,6 +353,7 @@ Renderer::Renderer(int device) : impl_(new Impl), device_(device) {
   int cnt = 0; cudaError_t e = cudaGetDeviceCount(&cnt);
   if (e != cudaSuccess || cnt == 0) { delete impl_; throw std::runtime_error("no CUDA device available: this renderer has no CPU fallback"); }
   CK(cudaSetDevice(device));
+  if (const char* sl = getenv("DRT_STACK_LIMIT")) CK(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atol(sl)));     // debugging aid
   cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); stream_ = st;
   CK(cudaMalloc(&impl_->ctr, sizeof(Counters))); CK(cudaMallocHost(&impl_->ctrHost, sizeof(Counters)));
   for (auto& e2 : impl_->ev) CK(cudaEventCreate(&e2));
