@@ -22,8 +22,22 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(scene="p3_t09.cli", cols=3840, rows=2160, spp=16)
-METRIC = "Mrays/s (all ray types), bun69k 4K 16spp"
+WORKLOADS = {
+    # BASELINE.json configs[1] (the configuration the metric is quoted on): bun69k in the p3_t09 wrapper
+    "bun69k": dict(scene="p3_t09.cli", cols=3840, rows=2160, spp=16, photons=-1, metric="Mrays/s (all ray types), bun69k 4K 16spp",
+                   desc="configs[1]: bun69k in the p3_t09 wrapper; mesh = bun500 subdivided 3x, 61824 tris, stand-in for the missing bun69k.cli"),
+    "t01": dict(scene="t01.cli", cols=3840, rows=2160, spp=16, photons=-1, metric="Mrays/s (all ray types), t01 4K 16spp", desc="configs[0]: two spheres, one point light"),
+    "sierp": dict(scene="p3_t11_sierp.cli", cols=3840, rows=2160, spp=16, photons=-1, metric="Mrays/s (all ray types), p3_t11_sierp 4K 16spp",
+                  desc="configs[2]: 21845 instances of the bun69k stand-in through the reference-topology instance BVH"),
+    "planets": dict(scene="plnts3ColsBunnies.cli", cols=3840, rows=2160, spp=16, photons=-1, metric="Mrays/s (all ray types), plnts3ColsBunnies 4K 16spp",
+                    desc="configs[3]: textured planets, bunny BVHs, reflection/refraction, spot + point lights"),
+    "box_caustics": dict(scene="box_caustics.cli", cols=3840, rows=2160, spp=16, photons=4000000, metric="Mrays/s (all ray types incl. photon segments), box caustics 4K 16spp",
+                         desc="configs[4]: Cornell wrapper around data/box.cli, caustic photon map k=80 r=0.05; photon pass inside every step"),
+    "box_gi": dict(scene="box_gi.cli", cols=3840, rows=2160, spp=16, photons=1000000, metric="Mrays/s (all ray types incl. photon segments), box diffuse-GI 4K 16spp",
+                   desc="configs[4] diffuse variant: diffuse photon map k=200 r=0.1; photon pass inside every step"),
+}
+WORKLOAD = dict(WORKLOADS["bun69k"])
+METRIC = WORKLOAD["metric"]
 CPU_TILE = (1728, 972, 1728 + 384, 972 + 216)      # bounded CPU sample: centre 384x216 tile of the 4K frame at 16 spp
 
 
@@ -70,7 +84,7 @@ def cpu_leg(threads, steps=1, warmup=0):
     from oracle import orc
     orc.build()
     w = WORKLOAD
-    o = orc.OracleScene(w["scene"], cols=w["cols"], rows=w["rows"], spp=w["spp"])
+    o = orc.OracleScene(w["scene"], cols=w["cols"], rows=w["rows"], spp=w["spp"], photons=min(w["photons"], 200000) if w["photons"] >= 0 else -1)
     best = None
     for i in range(warmup + steps):
         r = o.render(rect=CPU_TILE, threads=threads, want=("argb",))
@@ -89,7 +103,7 @@ def reference_arm(args):
     from oracle import orc
     orc.build()
     w = WORKLOAD
-    o = orc.OracleScene(w["scene"], cols=w["cols"], rows=w["rows"], spp=w["spp"])
+    o = orc.OracleScene(w["scene"], cols=w["cols"], rows=w["rows"], spp=w["spp"], photons=min(w["photons"], 200000) if w["photons"] >= 0 else -1)
     secs, rays = [], 0
     for i in range(args.warmup + args.steps):
         r = o.render(rect=CPU_TILE, threads=threads, want=("argb",))
@@ -114,7 +128,19 @@ def main():
     ap.add_argument("--accel", type=int, default=int(os.environ.get("DRT_ACCEL", "1")), help="0 reference-topology literal order, 1 reference-topology near-first (bit-identical results, default), 2 GPU LBVH")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="bun69k", choices=sorted(WORKLOADS))
+    ap.add_argument("--photons", type=int, default=None, help="photons cast per light for the photon workloads (sweep 1M..64M)")
+    ap.add_argument("--res", default=None, help="COLSxROWS override")
+    ap.add_argument("--spp", type=int, default=None)
     args = ap.parse_args()
+    global METRIC
+    WORKLOAD.clear(); WORKLOAD.update(WORKLOADS[args.workload]); METRIC = WORKLOAD["metric"]
+    if args.photons is not None and WORKLOAD["photons"] >= 0:
+        WORKLOAD["photons"] = args.photons
+    if args.res:
+        WORKLOAD["cols"], WORKLOAD["rows"] = (int(x) for x in args.res.lower().split("x"))
+    if args.spp:
+        WORKLOAD["spp"] = args.spp
     if args.impl == "reference":
         return reference_arm(args)
     args.warmup = max(args.warmup, 3)
@@ -134,7 +160,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = WORKLOAD
     ctx = drt.Context(device=local, cols=w["cols"], rows=w["rows"])
-    scene = drt.Scene.from_cli(ctx, w["scene"], spp=w["spp"], accel=args.accel)
+    scene = drt.Scene.from_cli(ctx, w["scene"], spp=w["spp"], photons=w["photons"], accel=args.accel)
+    has_photons = scene.info()["photon_kind"] != 0
     npix = w["cols"] * w["rows"]
     frame = torch.zeros(npix, dtype=torch.int32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
@@ -145,12 +172,17 @@ def main():
         torch.cuda.synchronize()
 
     def step():
+        if has_photons:      # the reference emits the map inside draw() (myScene.initRender, :1096-1099): it is part of the frame
+            stored, extra_launches = D.photon_pass(scene, w["photons"], world, rank, dist)
+        else:
+            extra_launches = 0
         if world == 1:
             st = scene.draw_device(0, npix, frame.data_ptr())
             out = frame
         else:
             st = scene.draw_device_chunks(world, rank, D.CHUNK_ROWS, frame.data_ptr())
             out = D.gather_frame(frame, w["rows"], w["cols"], world, rank, dist)
+        st.kernel_launches += extra_launches
         return st, out
 
     for _ in range(args.warmup):
@@ -173,6 +205,7 @@ def main():
             else:
                 r, l, tr = t[1].item(), t[2].item(), t[3].item()
             gpu_ms.append(ms); rays = int(r); launches = int(l); trace_ms += tr
+            stage = {"trace": st.ms_trace, "shade": st.ms_shade, "light": st.ms_light, "other": st.ms_other, "render_total": st.ms_total}
     clocks = cs.summary()
     ms_per_step = sum(gpu_ms) / len(gpu_ms)
     value = rays / (ms_per_step / 1e3) / 1e6
@@ -205,7 +238,7 @@ def main():
     if rank == 0:
         peaks, which = measured_peaks()
         cctx = drt.Context(device=local, cols=480, rows=270, counters=True)          # same camera/scene at 1/8 linear size: per-ray averages
-        cs2 = drt.Scene.from_cli(cctx, w["scene"], spp=w["spp"], accel=args.accel)
+        cs2 = drt.Scene.from_cli(cctx, w["scene"], spp=w["spp"], photons=min(w["photons"], 100000) if w["photons"] >= 0 else -1, accel=args.accel)
         _, cst = cs2.draw()
         r_all = cst.rays_primary + cst.rays_reflect + cst.rays_refract          # rays traced by k_trace (closest hit)
         box_per_ray, prim_per_ray = cst.box_tests_closest / r_all, cst.prim_tests_closest / r_all
@@ -235,10 +268,10 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 3), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "%s %dx%d %dspp (configs[1]: bun69k in the p3_t09 wrapper; mesh = bun500 subdivided 3x, 61824 tris, stand-in for the missing bun69k.cli)" % (w["scene"], w["cols"], w["rows"], w["spp"]),
+                "config": {"workload": "%s %dx%d %dspp%s (%s)" % (w["scene"], w["cols"], w["rows"], w["spp"], (", %d photons cast per light" % w["photons"]) if has_photons else "", w["desc"]),
                            "accel": ["reference-topology literal", "reference-topology fast", "lbvh"][args.accel], "l2": "flushed between timed iterations (256 MiB fill)", "partition": "interleaved 8-row chunks" if world > 1 else "single GPU",
                            "rays_per_frame": rays},
-                "frame_ms": round(ms_per_step, 3), "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
+                "frame_ms": round(ms_per_step, 3), "stages_ms_rank0_last_step": {k: round(v, 3) for k, v in stage.items()}, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()

@@ -12,6 +12,8 @@
 
 namespace drt {
 
+static thread_local unsigned long long g_kernelLaunches = 0;   // every launch of the build-side kernels (sort, scan, photon map, LBVH) bumps this; the renderer folds it into its stats
+
 #ifndef CK
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x); } while (0)
 #endif
@@ -62,11 +64,11 @@ static inline long long scanScratchWords(long long n) { long long w = 0; while (
 static inline void scanExclusiveU32(const uint32_t* in, uint32_t* out, long long n, uint32_t* scratch, cudaStream_t st) {
   if (n <= 0) return;
   long long tiles = (n + DRT_SCAN_TILE - 1) / DRT_SCAN_TILE;
-  if (tiles == 1) { k_scan_apply<<<1, 256, 0, st>>>(in, n, nullptr, out); return; }
+  if (tiles == 1) { k_scan_apply<<<1, 256, 0, st>>>(in, n, nullptr, out); ++g_kernelLaunches; return; }
   uint32_t* sums = scratch;
-  k_scan_tile_sums<<<(unsigned)tiles, 256, 0, st>>>(in, n, sums);
+  k_scan_tile_sums<<<(unsigned)tiles, 256, 0, st>>>(in, n, sums); ++g_kernelLaunches;
   scanExclusiveU32(sums, sums, tiles, scratch + tiles + 1, st);
-  k_scan_apply<<<(unsigned)tiles, 256, 0, st>>>(in, n, sums, out);
+  k_scan_apply<<<(unsigned)tiles, 256, 0, st>>>(in, n, sums, out); ++g_kernelLaunches;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -140,9 +142,9 @@ static inline int radixSortPairs(uint32_t* keys[2], uint32_t* vals[2], long long
   int cur = 0; if (n <= 0) return 0;
   const long long nb = radixBlocks(n);
   for (int shift = 0; shift < bits; shift += 8) {
-    k_radix_hist<<<(unsigned)nb, 256, 0, st>>>(keys[cur], n, shift, hist);
+    k_radix_hist<<<(unsigned)nb, 256, 0, st>>>(keys[cur], n, shift, hist); ++g_kernelLaunches;
     scanExclusiveU32(hist, hist, 256 * nb, scratch, st);
-    k_radix_scatter<<<(unsigned)nb, 256, 0, st>>>(keys[cur], (identity && shift == 0) ? nullptr : vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, hist);
+    k_radix_scatter<<<(unsigned)nb, 256, 0, st>>>(keys[cur], (identity && shift == 0) ? nullptr : vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, shift, hist); ++g_kernelLaunches;
     cur ^= 1;
   }
   if (bits <= 0 && identity) throw std::runtime_error("radixSortPairs: bits must be > 0");

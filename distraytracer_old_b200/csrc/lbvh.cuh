@@ -111,14 +111,14 @@ static inline int lbvhBuild(FTri* trisAll, int triStart, int nTris, const double
   sc.ensure((size_t)nTris);
   LbvhBox root; for (int k = 0; k < 3; ++k) { root.mn[k] = bmin[k]; root.mx[k] = bmax[k]; }
   FTri* range = trisAll + triStart;
-  k_lbvh_morton<<<(nTris + 255) / 256, 256, 0, st>>>(range, nTris, root, sc.keys[0]);
+  k_lbvh_morton<<<(nTris + 255) / 256, 256, 0, st>>>(range, nTris, root, sc.keys[0]); ++g_kernelLaunches;
   const int cur = radixSortPairs(sc.keys, sc.vals, nTris, 30, true, sc.hist, sc.scan, st);
-  k_lbvh_gather<<<(unsigned)(((long long)nTris * 8 + 255) / 256), 256, 0, st>>>(range, sc.vals[cur], nTris, sc.tmp);
+  k_lbvh_gather<<<(unsigned)(((long long)nTris * 8 + 255) / 256), 256, 0, st>>>(range, sc.vals[cur], nTris, sc.tmp); ++g_kernelLaunches;
   CK(cudaMemcpyAsync(range, sc.tmp, (size_t)nTris * sizeof(FTri), cudaMemcpyDeviceToDevice, st));
-  k_lbvh_leaves<<<(nLeaves + 255) / 256, 256, 0, st>>>(range, sc.keys[cur], nTris, nLeaves, sc.leafBox, sc.leafCode);
-  k_lbvh_hierarchy<<<(nLeaves - 1 + 255) / 256, 256, 0, st>>>(sc.leafCode, nLeaves, sc.child, sc.parentI, sc.parentL);
+  k_lbvh_leaves<<<(nLeaves + 255) / 256, 256, 0, st>>>(range, sc.keys[cur], nTris, nLeaves, sc.leafBox, sc.leafCode); ++g_kernelLaunches;
+  k_lbvh_hierarchy<<<(nLeaves - 1 + 255) / 256, 256, 0, st>>>(sc.leafCode, nLeaves, sc.child, sc.parentI, sc.parentL); ++g_kernelLaunches;
   CK(cudaMemsetAsync(sc.flags, 0, (size_t)nLeaves * 4, st));
-  k_lbvh_refit<<<(nLeaves + 255) / 256, 256, 0, st>>>(nLeaves, nTris, triStart, nodeBase, sc.child, sc.parentI, sc.parentL, sc.leafBox, sc.nodeBox, sc.flags, nodesOut);
+  k_lbvh_refit<<<(nLeaves + 255) / 256, 256, 0, st>>>(nLeaves, nTris, triStart, nodeBase, sc.child, sc.parentI, sc.parentL, sc.leafBox, sc.nodeBox, sc.flags, nodesOut); ++g_kernelLaunches;
   return nLeaves - 1;
 }
 

@@ -183,6 +183,12 @@ __global__ void k_photon_reorder(const PhotonRec* __restrict__ rec, const uint32
 // ---------------------------------------------------------------------------------------------------------------
 // gather
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef DRT_PH_PRECHECK
+#define DRT_PH_PRECHECK 1
+#endif
+#ifndef DRT_PH_CULL
+#define DRT_PH_CULL 0      // sphere-chord culling of cell rows: measured slower on B200 (profiles/r1_tuning.md) -- the per-row FP64 sqrt/divide costs more than the skipped cells
+#endif
 #define DRT_PH_BINS 256
 #define DRT_PH_LIST 128
 struct PhWarpShared { uint32_t hist[DRT_PH_BINS]; double listD2[DRT_PH_LIST]; uint32_t listIdx[DRT_PH_LIST]; uint32_t listN; uint32_t pad[3]; };
@@ -204,15 +210,32 @@ __device__ inline void phWarpGather(const DScene& S, D3 p, PhWarpShared& sh, dou
   if (empty) return;
   const double qscale = 4294967295.0 / r2;          // quantised key: monotone non-decreasing in d^2, < 2^32 for d^2 < r^2
   const double4* __restrict__ P = reinterpret_cast<const double4*>(S.phPos); const double4* __restrict__ W = reinterpret_cast<const double4*>(S.phPwr);
-  // visit every candidate of the 3x3 (or so) rows of cells; F(j, d2, q) is called for candidates with d2 < r2
+  // visit every candidate of the <= 3x3 rows of cells that the search sphere can reach; F(j, d2, q, ok) is called warp-wide, ok = d2 < r2.
+  // A row (cy, cz) is skipped when the sphere misses its y/z slab, and its x range is cut to the chord of the sphere at that distance
+  // (slab edges padded by 1e-9 cell: the cell index of a photon is a rounded quotient).
+  const double rr2 = rr * rr, pad = 1e-9 * cell;
   auto forEach = [&](auto&& F) {
-    for (int cz = lo[2]; cz <= hi[2]; ++cz) for (int cy = lo[1]; cy <= hi[1]; ++cy) {
-      const uint32_t row = ((uint32_t)cz * S.gridDim[1] + (uint32_t)cy) * S.gridDim[0];
-      const uint32_t a = S.cellStart[row + lo[0]], b = S.cellStart[row + hi[0] + 1];
-      for (uint32_t j0 = a; j0 < b; j0 += 32) {
-        const uint32_t j = j0 + lane; bool ok = j < b; double d2 = 0;
-        if (ok) { const double4 q = P[j]; const double dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z; d2 = dx * dx + dy * dy + dz * dz; ok = d2 < r2; }
-        F(j, d2, ok ? (uint32_t)(d2 * qscale) : 0u, ok);
+    for (int cz = lo[2]; cz <= hi[2]; ++cz) {
+      const double z0 = S.gridMin[2] + cz * cell, dz = fmax(0.0, fmax(z0 - pad - p.z, p.z - (z0 + cell + pad)));
+      for (int cy = lo[1]; cy <= hi[1]; ++cy) {
+        const double y0 = S.gridMin[1] + cy * cell, dy = fmax(0.0, fmax(y0 - pad - p.y, p.y - (y0 + cell + pad)));
+#if DRT_PH_CULL
+        const double rem2 = rr2 - dy * dy - dz * dz;
+        if (rem2 < 0) continue;
+        const double xr = sqrt(rem2) + pad;
+        int x0 = (int)floor((p.x - xr - S.gridMin[0]) / cell), x1 = (int)floor((p.x + xr - S.gridMin[0]) / cell);
+        x0 = x0 < lo[0] ? lo[0] : x0; x1 = x1 > hi[0] ? hi[0] : x1;
+        if (x1 < x0) continue;
+#else
+        (void)dy; (void)dz; const int x0 = lo[0], x1 = hi[0];
+#endif
+        const uint32_t row = ((uint32_t)cz * S.gridDim[1] + (uint32_t)cy) * S.gridDim[0];
+        const uint32_t a = S.cellStart[row + x0], b = S.cellStart[row + x1 + 1];
+        for (uint32_t j0 = a; j0 < b; j0 += 32) {
+          const uint32_t j = j0 + lane; bool ok = j < b; double d2 = 0;
+          if (ok) { const double4 q = P[j]; const double dx = p.x - q.x, dy2 = p.y - q.y, dz2 = p.z - q.z; d2 = dx * dx + dy2 * dy2 + dz2 * dz2; ok = d2 < r2; }
+          F(j, d2, ok ? (uint32_t)(d2 * qscale) : 0u, ok);
+        }
       }
     }
   };
@@ -282,6 +305,21 @@ __device__ inline void phWarpGather(const DScene& S, D3 p, PhWarpShared& sh, dou
   sum[0] = s0; sum[1] = s1; sum[2] = s2; dmax2 = mx;
 }
 
+// cheap per-lane test: does any cell the search sphere's bounding cube overlaps hold a photon at all?  (sparse caustic maps: most queries do not)
+__device__ inline bool phAnyCandidate(const DScene& S, D3 p) {
+  if (S.numPhotons == 0) return false;
+  const double rr = sqrt(S.g.phMaxDist2) * 1.0000001, cell = S.cellSize; int lo[3], hi[3]; const double pp[3] = {p.x, p.y, p.z};
+  for (int k = 0; k < 3; ++k) {
+    const double a = floor((pp[k] - rr - S.gridMin[k]) / cell), b = floor((pp[k] + rr - S.gridMin[k]) / cell); const int dim = (int)S.gridDim[k];
+    if (!(b >= 0) || !(a <= dim - 1)) return false;
+    lo[k] = a < 0 ? 0 : (int)a; hi[k] = b > dim - 1 ? dim - 1 : (int)b;
+  }
+  for (int cz = lo[2]; cz <= hi[2]; ++cz) for (int cy = lo[1]; cy <= hi[1]; ++cy) {
+    const uint32_t row = ((uint32_t)cz * S.gridDim[1] + (uint32_t)cy) * S.gridDim[0];
+    if (S.cellStart[row + hi[0] + 1] > S.cellStart[row + lo[0]]) return true;
+  }
+  return false;
+}
 // One warp serves the 32 surface records it owns, one query at a time. Runs between k_shade (local = ambient) and k_light
 // (local += direct), which is the reference's accumulation order (myObjShader.java:413-425).
 __global__ void __launch_bounds__(128) k_photon_gather(const __grid_constant__ DScene S, long long n, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, Counters* ctr) {
@@ -289,7 +327,11 @@ __global__ void __launch_bounds__(128) k_photon_gather(const __grid_constant__ D
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; const unsigned lane = threadIdx.x & 31;
   bool needs = false; D3 loc = d3(0, 0, 0); int shIdx = -1;
   if (i < n) { const SurfRec s = surf[i]; if (s.valid) { shIdx = s.shader; const FShader& sh = S.shaders[shIdx];
-      needs = !(sh.flags & SF_SIMPLE) && (sh.KRefl == 0.0) && (sh.flags & SF_USE_PHOTON); loc = d3(s.loc[0], s.loc[1], s.loc[2]); } }
+      needs = !(sh.flags & SF_SIMPLE) && (sh.KRefl == 0.0) && (sh.flags & SF_USE_PHOTON); loc = d3(s.loc[0], s.loc[1], s.loc[2]); 
+#if DRT_PH_PRECHECK
+      needs = needs && phAnyCandidate(S, loc);
+#endif
+    } }
   unsigned mask = __ballot_sync(0xffffffffu, needs);
   while (mask) {
     const int src = __ffs(mask) - 1; mask &= mask - 1;
@@ -322,9 +364,16 @@ struct PhotonMap {
   PhotonRec* rec = nullptr; size_t recCap = 0;                  // canonical-order records (emission output / grid input)
   double4 *pos = nullptr, *pwr = nullptr; uint32_t* cellStart = nullptr; size_t sortedCap = 0, cellCap = 0;
   PhGrid grid{}; float msEmit = 0, msBuild = 0;
+  // grow-only scratch (no cudaMalloc / cudaFree on the per-frame path: they cost tens to hundreds of ms when they hit the driver's slow path)
+  struct Scratch { void* p = nullptr; size_t cap = 0; template <class T> T* get(size_t n) { const size_t b = n * sizeof(T); if (b > cap) { cudaFree(p); p = nullptr; cap = b + b / 4 + 4096; CK(cudaMalloc(&p, cap)); } return reinterpret_cast<T*>(p); }
+                   void release() { cudaFree(p); p = nullptr; cap = 0; } };
+  Scratch sSlots, sCnt, sOff, sScan, sKeys[2], sVals[2], sHist, sBounds; cudaEvent_t evA = nullptr, evB = nullptr;
+  void events() { if (!evA) { CK(cudaEventCreate(&evA)); CK(cudaEventCreate(&evB)); } }
 
   void reset() { built = false; emitted = false; count = 0; segments = 0; }
-  void release() { cudaFree(rec); cudaFree(pos); cudaFree(pwr); cudaFree(cellStart); rec = nullptr; pos = pwr = nullptr; cellStart = nullptr; recCap = sortedCap = cellCap = 0; reset(); }
+  void release() { cudaFree(rec); cudaFree(pos); cudaFree(pwr); cudaFree(cellStart); rec = nullptr; pos = pwr = nullptr; cellStart = nullptr; recCap = sortedCap = cellCap = 0; reset();
+    sSlots.release(); sCnt.release(); sOff.release(); sScan.release(); sHist.release(); sBounds.release(); for (int k = 0; k < 2; ++k) { sKeys[k].release(); sVals[k].release(); }
+    if (evA) { cudaEventDestroy(evA); cudaEventDestroy(evB); evA = evB = nullptr; } }
   void ensureRec(size_t n, cudaStream_t st) {
     if (n <= recCap) return;
     size_t nc = n + n / 2 + 4096; PhotonRec* q = nullptr; CK(cudaMalloc(&q, nc * sizeof(PhotonRec)));
@@ -339,27 +388,23 @@ struct PhotonMap {
     const int maxStore = ds.g.photonKind == 1 ? 1 : (ds.g.numPhotonRays + 1);
     const long long chunkPhotons = std::max<long long>(1, (1ll << 21) / nl);
     const long long maxThreads = std::min(chunkPhotons, i1 - i0) * nl;
-    PhotonRec* slots = nullptr; uint32_t *cnt = nullptr, *off = nullptr, *scratch = nullptr;
-    CK(cudaMalloc(&slots, (size_t)maxThreads * maxStore * sizeof(PhotonRec))); CK(cudaMalloc(&cnt, (size_t)(maxThreads + 1) * 4)); CK(cudaMalloc(&off, (size_t)(maxThreads + 1) * 4));
-    CK(cudaMalloc(&scratch, (size_t)scanScratchWords(maxThreads + 1) * 4));
-    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventRecord(e0, st));
+    PhotonRec* slots = sSlots.get<PhotonRec>((size_t)maxThreads * maxStore); uint32_t* cnt = sCnt.get<uint32_t>((size_t)maxThreads + 1); uint32_t* off = sOff.get<uint32_t>((size_t)maxThreads + 1);
+    uint32_t* scratch = sScan.get<uint32_t>((size_t)scanScratchWords(maxThreads + 1));
+    events(); cudaEvent_t e0 = evA, e1 = evB; CK(cudaEventRecord(e0, st));
     CK(cudaMemsetAsync(&ctr->pad, 0, sizeof(unsigned long long), st));
-    try {
-      for (long long c0 = i0; c0 < i1; c0 += chunkPhotons) {
-        const long long np = std::min(chunkPhotons, i1 - c0), nt = np * nl;
-        CK(cudaMemsetAsync(cnt + nt, 0, 4, st));
-        k_photon_emit<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(ds, c0, nt, maxStore, slots, cnt, ctr);
-        scanExclusiveU32(cnt, off, nt + 1, scratch, st);
-        uint32_t total = 0; CK(cudaMemcpyAsync(&total, off + nt, 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-        ensureRec(count + total, st);
-        if (total) k_photon_compact<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(nt, maxStore, slots, cnt, off, rec + count);
-        count += total;
-      }
-      CK(cudaMemcpyAsync(ctrHost, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-      CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
-      segments = ctrHost->pad; CK(cudaEventElapsedTime(&msEmit, e0, e1));
-    } catch (...) { cudaFree(slots); cudaFree(cnt); cudaFree(off); cudaFree(scratch); cudaEventDestroy(e0); cudaEventDestroy(e1); throw; }
-    cudaFree(slots); cudaFree(cnt); cudaFree(off); cudaFree(scratch); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    for (long long c0 = i0; c0 < i1; c0 += chunkPhotons) {
+      const long long np = std::min(chunkPhotons, i1 - c0), nt = np * nl;
+      CK(cudaMemsetAsync(cnt + nt, 0, 4, st));
+      k_photon_emit<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(ds, c0, nt, maxStore, slots, cnt, ctr); ++g_kernelLaunches;
+      scanExclusiveU32(cnt, off, nt + 1, scratch, st);
+      uint32_t total = 0; CK(cudaMemcpyAsync(&total, off + nt, 4, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+      ensureRec(count + total, st);
+      if (total) { k_photon_compact<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(nt, maxStore, slots, cnt, off, rec + count); ++g_kernelLaunches; }
+      count += total;
+    }
+    CK(cudaMemcpyAsync(ctrHost, ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+    segments = ctrHost->pad; CK(cudaEventElapsedTime(&msEmit, e0, e1));
   }
   // replace the record store with `n` records that already live on the device (multi-GPU: the all-gathered set)
   void setRecords(const PhotonRec* srcDev, unsigned long long n, cudaStream_t st) {
@@ -372,12 +417,12 @@ struct PhotonMap {
     ds.numPhotons = 0; ds.phPos = nullptr; ds.phPwr = nullptr; ds.cellStart = nullptr; ds.cellEnd = nullptr; built = true; msBuild = 0;
     if (count == 0) return;
     if (count >= 0xFFFFFFF0ull) throw std::runtime_error("photon map larger than 2^32 records");
-    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventRecord(e0, st));
+    events(); cudaEvent_t e0 = evA, e1 = evB; CK(cudaEventRecord(e0, st));
     const long long n = (long long)count;
     // bounds
-    const int nbB = 592; double* bmm = nullptr; CK(cudaMalloc(&bmm, nbB * 6 * sizeof(double)));
-    k_photon_bounds<<<nbB, 256, 0, st>>>(rec, n, bmm);
-    std::vector<double> hb(nbB * 6); CK(cudaMemcpyAsync(hb.data(), bmm, hb.size() * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); cudaFree(bmm);
+    const int nbB = 592; double* bmm = sBounds.get<double>((size_t)nbB * 6);
+    k_photon_bounds<<<nbB, 256, 0, st>>>(rec, n, bmm); ++g_kernelLaunches;
+    std::vector<double> hb(nbB * 6); CK(cudaMemcpyAsync(hb.data(), bmm, hb.size() * 8, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
     double mn[3] = {DRT_DMAX, DRT_DMAX, DRT_DMAX}, mx[3] = {-DRT_DMAX, -DRT_DMAX, -DRT_DMAX};
     for (int b = 0; b < nbB; ++b) for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], hb[b * 6 + k]); mx[k] = std::max(mx[k], hb[b * 6 + 3 + k]); }
     double cell = std::sqrt(ds.g.phMaxDist2); if (!(cell > 0)) cell = 1e-3;
@@ -389,20 +434,19 @@ struct PhotonMap {
     }
     G.cell = cell; for (int k = 0; k < 3; ++k) G.gmin[k] = mn[k]; G.nCells = G.dim[0] * G.dim[1] * G.dim[2]; grid = G;
     // keys + per-cell counts, cellStart = exclusive scan (nCells + 1 entries: cellStart[nCells] = n)
-    if ((size_t)G.nCells + 1 > cellCap) { cudaFree(cellStart); cellCap = (size_t)G.nCells + 1; CK(cudaMalloc(&cellStart, cellCap * 4)); }
+    if ((size_t)G.nCells + 1 > cellCap) { cudaFree(cellStart); cellCap = (size_t)G.nCells + 1 + (size_t)G.nCells / 4; CK(cudaMalloc(&cellStart, cellCap * 4)); }
     if ((size_t)n > sortedCap) { cudaFree(pos); cudaFree(pwr); sortedCap = (size_t)n + (size_t)n / 8 + 1024; CK(cudaMalloc(&pos, sortedCap * sizeof(double4))); CK(cudaMalloc(&pwr, sortedCap * sizeof(double4))); }
-    uint32_t *keys[2], *vals[2], *hist, *scratch; const long long nb = radixBlocks(n);
-    for (int k = 0; k < 2; ++k) { CK(cudaMalloc(&keys[k], (size_t)n * 4)); CK(cudaMalloc(&vals[k], (size_t)n * 4)); }
+    uint32_t *keys[2], *vals[2]; const long long nb = radixBlocks(n);
+    for (int k = 0; k < 2; ++k) { keys[k] = sKeys[k].get<uint32_t>((size_t)n); vals[k] = sVals[k].get<uint32_t>((size_t)n); }
     const long long scanWords = std::max(scanScratchWords(256 * nb), scanScratchWords((long long)G.nCells + 1));
-    CK(cudaMalloc(&hist, (size_t)256 * nb * 4)); CK(cudaMalloc(&scratch, (size_t)scanWords * 4));
+    uint32_t* hist = sHist.get<uint32_t>((size_t)256 * nb); uint32_t* scratch = sScan.get<uint32_t>((size_t)scanWords);
     CK(cudaMemsetAsync(cellStart, 0, ((size_t)G.nCells + 1) * 4, st));
-    k_photon_cellkeys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, n, G, keys[0], cellStart);
+    k_photon_cellkeys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, n, G, keys[0], cellStart); ++g_kernelLaunches;
     scanExclusiveU32(cellStart, cellStart, (long long)G.nCells + 1, scratch, st);
     int bits = 1; while ((1ull << bits) < (unsigned long long)G.nCells) ++bits;
     const int cur = radixSortPairs(keys, vals, n, bits, true, hist, scratch, st);
-    k_photon_reorder<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, vals[cur], n, pos, pwr);
+    k_photon_reorder<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, vals[cur], n, pos, pwr); ++g_kernelLaunches;
     CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError()); CK(cudaEventElapsedTime(&msBuild, e0, e1));
-    for (int k = 0; k < 2; ++k) { cudaFree(keys[k]); cudaFree(vals[k]); } cudaFree(hist); cudaFree(scratch); cudaEventDestroy(e0); cudaEventDestroy(e1);
     ds.numPhotons = (uint32_t)n; ds.phPos = reinterpret_cast<const double*>(pos); ds.phPwr = reinterpret_cast<const double*>(pwr); ds.cellStart = cellStart; ds.cellEnd = nullptr;
     for (int k = 0; k < 3; ++k) { ds.gridDim[k] = G.dim[k]; ds.gridMin[k] = G.gmin[k]; } ds.cellSize = G.cell;
   }

@@ -434,6 +434,7 @@ void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank,
   pm.chunkPix = (pm.world == 1) ? (pm.totalPix > 0 ? pm.totalPix : 1) : (long long)chunkRows * g_.cols;
   if (pm.world > 1) { long long nChunks = (g_.rows + chunkRows - 1) / chunkRows, mine = (nChunks - rank + world - 1) / world; pix0 = 0; pix1 = mine * pm.chunkPix; }
   if (!I.ds.prims) throw std::runtime_error("render called before a scene was uploaded");
+  const unsigned long long buildLaunches0 = g_kernelLaunches;
   if (g_.photonKind != 0 && !I.photons.built) { if (!I.photons.emitted) I.photons.emitRange(I.ds, 0, g_.numPhotonsCast, I.ctr, I.ctrHost, st); I.photons.buildGrid(I.ds, st); }
   const int spp = g_.spp < 1 ? 1 : g_.spp;
   long long pixPerBatch = batchRays_ / spp; if (pixPerBatch < 1) pixPerBatch = 1;
@@ -482,6 +483,7 @@ void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank,
   CK(cudaEventRecord(I.ev[5], st)); CK(cudaStreamSynchronize(st));
   float tot; CK(cudaEventElapsedTime(&tot, I.ev[0], I.ev[5]));
   CK(cudaGetLastError());
+  rs.kernelLaunches += g_kernelLaunches - buildLaunches0;      // photon emission / grid build done inside this call
   rs.msTrace = msT; rs.msShade = msS; rs.msLight = msL; rs.msTotal = tot; rs.msOther = tot - msT - msS - msL;
   if (stats) *stats = rs;
 }
@@ -506,17 +508,18 @@ void Renderer::renderToHost(int32_t* argbHost, int32_t* hitPrimHost, int32_t* hi
 
 double hostPhiloxU01(uint64_t seed, uint32_t stream, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return philoxU01(seed, stream, a, b, c, d); }
 void Renderer::emitPhotons(RenderStats* stats) {
-  CK(cudaSetDevice(device_)); Impl& I = *impl_;
+  CK(cudaSetDevice(device_)); Impl& I = *impl_; const unsigned long long l0 = g_kernelLaunches;
   if (g_.photonKind != 0 && !I.photons.built) I.photons.emitAndBuild(I.ds, I.ctr, I.ctrHost, (cudaStream_t)stream_);
-  if (stats) { stats->photonsStored = I.photons.count; stats->photonSeg = I.photons.segments; stats->msTrace = I.photons.msEmit; stats->msOther = I.photons.msBuild; stats->msTotal = I.photons.msEmit + I.photons.msBuild; }
+  if (stats) { stats->kernelLaunches = g_kernelLaunches - l0; stats->photonsStored = I.photons.count; stats->photonSeg = I.photons.segments; stats->msTrace = I.photons.msEmit; stats->msOther = I.photons.msBuild; stats->msTotal = I.photons.msEmit + I.photons.msBuild; }
 }
 // multi-GPU split: emit photon indices [i0, i1) of every light (no grid build); export / import the canonical-order records on the device
 void Renderer::emitPhotonsRange(long long i0, long long i1, RenderStats* stats) {
   CK(cudaSetDevice(device_)); Impl& I = *impl_;
   if (g_.photonKind == 0) { I.photons.reset(); return; }
   if (i0 < 0 || i1 > g_.numPhotonsCast || i0 > i1) throw std::runtime_error("photon index range outside [0, photons cast]");
+  const unsigned long long l0 = g_kernelLaunches;
   I.photons.emitRange(I.ds, i0, i1, I.ctr, I.ctrHost, (cudaStream_t)stream_);
-  if (stats) { stats->photonsStored = I.photons.count; stats->photonSeg = I.photons.segments; stats->msTrace = I.photons.msEmit; stats->msTotal = I.photons.msEmit; }
+  if (stats) { stats->kernelLaunches = g_kernelLaunches - l0; stats->photonsStored = I.photons.count; stats->photonSeg = I.photons.segments; stats->msTrace = I.photons.msEmit; stats->msTotal = I.photons.msEmit; }
 }
 long long Renderer::exportPhotonsDevice(double* dst6Dev, long long cap) {
   CK(cudaSetDevice(device_)); Impl& I = *impl_; cudaStream_t st = (cudaStream_t)stream_;
@@ -527,8 +530,9 @@ long long Renderer::exportPhotonsDevice(double* dst6Dev, long long cap) {
 void Renderer::buildPhotonsFromDevice(const double* src6Dev, long long n, RenderStats* stats) {
   CK(cudaSetDevice(device_)); Impl& I = *impl_; cudaStream_t st = (cudaStream_t)stream_;
   if (n < 0 || (n > 0 && !src6Dev)) throw std::runtime_error("bad photon record buffer");
+  const unsigned long long l0 = g_kernelLaunches;
   I.photons.setRecords(reinterpret_cast<const PhotonRec*>(src6Dev), (unsigned long long)n, st); I.photons.buildGrid(I.ds, st);
-  if (stats) { stats->photonsStored = I.photons.count; stats->msOther = I.photons.msBuild; stats->msTotal = I.photons.msBuild; }
+  if (stats) { stats->kernelLaunches = g_kernelLaunches - l0; stats->photonsStored = I.photons.count; stats->msOther = I.photons.msBuild; stats->msTotal = I.photons.msBuild; }
 }
 void Renderer::probePhotons(long long n, const double* ptsHost, double* out5Host) {
   CK(cudaSetDevice(device_)); Impl& I = *impl_; cudaStream_t st = (cudaStream_t)stream_;

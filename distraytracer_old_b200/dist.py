@@ -64,3 +64,42 @@ def gather_frame(local_full, rows, cols, world, rank, dist=None, chunk_rows=CHUN
         v = ridx >= 0
         frame[ridx[v]] = out[r * packed.numel():(r + 1) * packed.numel()][v]
     return frame
+
+
+def allgather_records(local, dist, world):
+    """All-gather of variable-length record blocks ([n_r, k] tensors, same dtype/device on every rank) in RANK ORDER.
+    Counts are exchanged first, blocks are padded to the longest one (all_gather_into_tensor needs equal sizes), then compacted.
+    Returns (tensor [sum n_r, k], counts). Works with NCCL (CUDA tensors) and gloo (CPU tensors)."""
+    import torch
+    if world == 1:
+        return local, [int(local.shape[0])]
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    m = max(max(counts), 1)
+    k = local.shape[1]
+    padded = torch.zeros((m, k), dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    out = torch.empty((world * m, k), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded)
+    return torch.cat([out[r * m:r * m + counts[r]] for r in range(world)]).contiguous(), counts
+
+
+def photon_pass(scene, n_cast, world, rank, dist=None):
+    """Photon map of a photon scene on `world` GPUs: rank r emits photon indices photon_range(n_cast, world, r) of every light, the
+    canonical-order records are all-gathered over NCCL, and every rank builds the full grid (the reference emits serially,
+    myScene.java:961,1009).  Bit-identical to the single-GPU map for any world size.  Returns (stored photons, photon-side kernel launches of this rank)."""
+    import torch
+    if world == 1:
+        st = scene.emit_photons_range(0, n_cast)          # always re-emits; the grid is built by the next render call
+        return int(st.photons_stored), int(st.kernel_launches)
+    i0, i1 = photon_range(n_cast, world, rank)
+    st = scene.emit_photons_range(i0, i1)
+    cnt = int(st.photons_stored)
+    buf = torch.empty((max(cnt, 1), 6), dtype=torch.float64, device="cuda")
+    scene.photons_export_device(buf.data_ptr(), cnt)
+    allrec, _ = allgather_records(buf[:cnt], dist, world)
+    torch.cuda.current_stream().synchronize()            # the library works on its own stream
+    st2 = scene.photons_build_device(allrec.data_ptr(), int(allrec.shape[0]))
+    return int(allrec.shape[0]), int(st.kernel_launches) + int(st2.kernel_launches)

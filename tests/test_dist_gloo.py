@@ -25,6 +25,19 @@ WORKER = textwrap.dedent("""
         print("GATHER_OK")
     else:
         assert frame is None
+    # photon exchange: ranks own contiguous photon-index ranges with a different number of stored records each; the gathered set must be
+    # the rank-order concatenation (== the single-GPU canonical order)
+    n_cast = 1003
+    i0, i1 = D.photon_range(n_cast, world, rank)
+    mine = torch.stack([torch.arange(i0, i1, dtype=torch.float64) * 10 + k for k in range(6)], dim=1)[::(2 + rank)].contiguous()   # ragged counts
+    allrec, counts = D.allgather_records(mine, dist, world)
+    want = torch.cat([torch.stack([torch.arange(*D.photon_range(n_cast, world, r), dtype=torch.float64) * 10 + k for k in range(6)], dim=1)[::(2 + r)] for r in range(world)])
+    assert counts == [len(range(*D.photon_range(n_cast, world, r))[::(2 + r)]) for r in range(world)]
+    assert torch.equal(allrec, want), "gathered photon records differ"
+    empty, c0 = D.allgather_records(mine[:0], dist, world)          # nobody stored anything
+    assert empty.shape[0] == 0 and c0 == [0] * world
+    if rank == 0:
+        print("PHOTONS_OK")
     dist.barrier(); dist.destroy_process_group()
 """) % ROOT
 
@@ -35,4 +48,4 @@ def test_frame_gather_world2(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29541", str(w)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "GATHER_OK" in r.stdout
+    assert "GATHER_OK" in r.stdout and "PHOTONS_OK" in r.stdout
