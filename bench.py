@@ -163,7 +163,7 @@ def main():
     scene = drt.Scene.from_cli(ctx, w["scene"], spp=w["spp"], photons=w["photons"], accel=args.accel)
     has_photons = scene.info()["photon_kind"] != 0
     npix = w["cols"] * w["rows"]
-    frame = torch.zeros(npix, dtype=torch.int32, device="cuda")
+    frame = torch.zeros(D.padded_pixels(w["rows"], w["cols"], world), dtype=torch.int32, device="cuda")   # padded to whole chunks per rank: the gather packs by view
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
     def barrier():
@@ -178,7 +178,7 @@ def main():
             extra_launches = 0
         if world == 1:
             st = scene.draw_device(0, npix, frame.data_ptr())
-            out = frame
+            out = frame[:npix]
         else:
             st = scene.draw_device_chunks(world, rank, D.CHUNK_ROWS, frame.data_ptr())
             out = D.gather_frame(frame, w["rows"], w["cols"], world, rank, dist)
@@ -207,6 +207,10 @@ def main():
             gpu_ms.append(ms); rays = int(r); launches = int(l); trace_ms += tr
             stage = {"trace": st.ms_trace, "shade": st.ms_shade, "light": st.ms_light, "other": st.ms_other, "render_total": st.ms_total}
     clocks = cs.summary()
+    frame_crc = None
+    if rank == 0 and out is not None:      # identical for every GPU count (sampler keyed by absolute pixel, canonical photon order)
+        import zlib
+        frame_crc = "%08x" % (zlib.crc32(out.cpu().numpy().tobytes()) & 0xffffffff)
     ms_per_step = sum(gpu_ms) / len(gpu_ms)
     value = rays / (ms_per_step / 1e3) / 1e6
 
@@ -271,7 +275,7 @@ def main():
                 "config": {"workload": "%s %dx%d %dspp%s (%s)" % (w["scene"], w["cols"], w["rows"], w["spp"], (", %d photons cast per light" % w["photons"]) if has_photons else "", w["desc"]),
                            "accel": ["reference-topology literal", "reference-topology fast", "lbvh"][args.accel], "l2": "flushed between timed iterations (256 MiB fill)", "partition": "interleaved 8-row chunks" if world > 1 else "single GPU",
                            "rays_per_frame": rays},
-                "frame_ms": round(ms_per_step, 3), "stages_ms_rank0_last_step": {k: round(v, 3) for k, v in stage.items()}, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
+                "frame_ms": round(ms_per_step, 3), "frame_crc32": frame_crc, "stages_ms_rank0_last_step": {k: round(v, 3) for k, v in stage.items()}, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()

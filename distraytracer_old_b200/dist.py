@@ -44,26 +44,33 @@ def photon_range(n_cast, world, rank):
     return (n_cast * rank) // world, (n_cast * (rank + 1)) // world
 
 
+def padded_pixels(rows, cols, world, chunk_rows=CHUNK_ROWS):
+    """Pixels of a frame buffer padded so that every rank owns the same number of whole chunks (>= rows*cols)."""
+    return packed_size(rows, cols, world, chunk_rows) * world
+
+
 def gather_frame(local_full, rows, cols, world, rank, dist=None, chunk_rows=CHUNK_ROWS):
-    """local_full: flat int32 torch tensor (rows*cols) holding this rank's chunks at their absolute positions.
-    Returns the assembled frame on rank 0 (None elsewhere).  Works with NCCL (CUDA tensors) and gloo (CPU tensors)."""
+    """local_full: flat int32 torch tensor holding this rank's chunks at their absolute positions (rows*cols entries, or
+    padded_pixels(...) entries -- the padded form avoids a copy).  Chunk c lives on rank c % world, so the buffer viewed as
+    [chunks_per_rank, world, chunk_pixels] has this rank's share at [:, rank, :]: one strided copy packs it, one all_gather_into_tensor
+    moves it, one permuted copy unpacks it.  Returns the assembled rows*cols frame on rank 0 (None elsewhere).
+    Works with NCCL (CUDA tensors) and gloo (CPU tensors)."""
     import torch
     if world == 1:
-        return local_full
-    idx = torch.from_numpy(pack_index(rows, cols, world, rank, chunk_rows)).to(local_full.device)
-    valid = idx >= 0
-    packed = torch.zeros(idx.numel(), dtype=local_full.dtype, device=local_full.device)
-    packed[valid] = local_full[idx[valid]]
-    out = torch.empty(world * packed.numel(), dtype=local_full.dtype, device=local_full.device)
-    dist.all_gather_into_tensor(out, packed)
+        return local_full[:rows * cols]
+    chunk_pix = chunk_rows * cols
+    per_rank = packed_size(rows, cols, world, chunk_rows) // chunk_pix
+    total = per_rank * world * chunk_pix
+    buf = local_full
+    if buf.numel() < total:
+        buf = torch.zeros(total, dtype=local_full.dtype, device=local_full.device)
+        buf[:local_full.numel()] = local_full
+    packed = buf[:total].view(per_rank, world, chunk_pix)[:, rank, :].contiguous()
+    out = torch.empty((world, per_rank, chunk_pix), dtype=buf.dtype, device=buf.device)
+    dist.all_gather_into_tensor(out.view(-1), packed.view(-1))
     if rank != 0:
         return None
-    frame = torch.zeros(rows * cols, dtype=local_full.dtype, device=local_full.device)
-    for r in range(world):
-        ridx = torch.from_numpy(pack_index(rows, cols, world, r, chunk_rows)).to(local_full.device)
-        v = ridx >= 0
-        frame[ridx[v]] = out[r * packed.numel():(r + 1) * packed.numel()][v]
-    return frame
+    return out.permute(1, 0, 2).reshape(-1)[:rows * cols]
 
 
 def allgather_records(local, dist, world):
