@@ -196,24 +196,29 @@ struct PhWarpShared { uint32_t hist[DRT_PH_BINS]; double listD2[DRT_PH_LIST]; ui
 // Sum of the powers of the k nearest photons with d^2 < r^2 around p, and the largest of their d^2 -- computed by one warp.
 // Selection = radix select on a 32-bit quantisation of d^2 (monotone in d^2), 8 bits per level over the candidate rows of the grid,
 // finished exactly (double d^2, index tie-break) on the short list of the boundary bin.
-__device__ inline void phWarpGather(const DScene& S, D3 p, PhWarpShared& sh, double sum[3], double& dmax2, unsigned long long* visited) {
+// cells the bounding cube of the search sphere overlaps (radius inflated by 1e-7 so that no photon with d^2 < r^2 can sit in a cell outside
+// the range whatever the rounding of its own cell index); false when the cube misses the grid
+__device__ __forceinline__ bool phCellRange(const DScene& S, D3 p, int lo[3], int hi[3]) {
+  const double rr = sqrt(S.g.phMaxDist2) * 1.0000001, cell = S.cellSize; const double pp[3] = {p.x, p.y, p.z}; bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double a = floor((pp[k] - rr - S.gridMin[k]) / cell), b = floor((pp[k] + rr - S.gridMin[k]) / cell); const int dim = (int)S.gridDim[k];
+    if (!(b >= 0) || !(a <= dim - 1)) ok = false;
+    lo[k] = a < 0 ? 0 : (a > dim - 1 ? dim - 1 : (int)a); hi[k] = b > dim - 1 ? dim - 1 : (b < 0 ? 0 : (int)b);
+  }
+  return ok;
+}
+__device__ inline void phWarpGather(const DScene& S, D3 p, const int lo[3], const int hi[3], PhWarpShared& sh, double sum[3], double& dmax2, unsigned long long* visited) {
   const unsigned lane = threadIdx.x & 31; const double r2 = S.g.phMaxDist2; const int K = S.g.kNhood;
   sum[0] = sum[1] = sum[2] = 0; dmax2 = 0;
   if (S.numPhotons == 0 || K <= 0) return;
-  const double rr = sqrt(r2) * 1.0000001, cell = S.cellSize;
-  int lo[3], hi[3]; const double pp[3] = {p.x, p.y, p.z}; bool empty = false;
-  for (int k = 0; k < 3; ++k) {
-    double a = floor((pp[k] - rr - S.gridMin[k]) / cell), b = floor((pp[k] + rr - S.gridMin[k]) / cell); const int dim = (int)S.gridDim[k];
-    if (!(b >= 0) || !(a <= dim - 1)) empty = true;
-    lo[k] = a < 0 ? 0 : (int)a; hi[k] = b > dim - 1 ? dim - 1 : (int)b;
-  }
-  if (empty) return;
+  const double cell = S.cellSize; (void)cell;
   const double qscale = 4294967295.0 / r2;          // quantised key: monotone non-decreasing in d^2, < 2^32 for d^2 < r^2
   const double4* __restrict__ P = reinterpret_cast<const double4*>(S.phPos); const double4* __restrict__ W = reinterpret_cast<const double4*>(S.phPwr);
   // visit every candidate of the <= 3x3 rows of cells that the search sphere can reach; F(j, d2, q, ok) is called warp-wide, ok = d2 < r2.
   // A row (cy, cz) is skipped when the sphere misses its y/z slab, and its x range is cut to the chord of the sphere at that distance
   // (slab edges padded by 1e-9 cell: the cell index of a photon is a rounded quotient).
-  const double rr2 = rr * rr, pad = 1e-9 * cell;
+  const double rr2 = r2 * 1.0000003, pad = 1e-9 * cell; (void)rr2; (void)pad;
   auto forEach = [&](auto&& F) {
     for (int cz = lo[2]; cz <= hi[2]; ++cz) {
       const double z0 = S.gridMin[2] + cz * cell, dz = fmax(0.0, fmax(z0 - pad - p.z, p.z - (z0 + cell + pad)));
@@ -306,14 +311,7 @@ __device__ inline void phWarpGather(const DScene& S, D3 p, PhWarpShared& sh, dou
 }
 
 // cheap per-lane test: does any cell the search sphere's bounding cube overlaps hold a photon at all?  (sparse caustic maps: most queries do not)
-__device__ inline bool phAnyCandidate(const DScene& S, D3 p) {
-  if (S.numPhotons == 0) return false;
-  const double rr = sqrt(S.g.phMaxDist2) * 1.0000001, cell = S.cellSize; int lo[3], hi[3]; const double pp[3] = {p.x, p.y, p.z};
-  for (int k = 0; k < 3; ++k) {
-    const double a = floor((pp[k] - rr - S.gridMin[k]) / cell), b = floor((pp[k] + rr - S.gridMin[k]) / cell); const int dim = (int)S.gridDim[k];
-    if (!(b >= 0) || !(a <= dim - 1)) return false;
-    lo[k] = a < 0 ? 0 : (int)a; hi[k] = b > dim - 1 ? dim - 1 : (int)b;
-  }
+__device__ inline bool phAnyCandidate(const DScene& S, const int lo[3], const int hi[3]) {
   for (int cz = lo[2]; cz <= hi[2]; ++cz) for (int cy = lo[1]; cy <= hi[1]; ++cy) {
     const uint32_t row = ((uint32_t)cz * S.gridDim[1] + (uint32_t)cy) * S.gridDim[0];
     if (S.cellStart[row + hi[0] + 1] > S.cellStart[row + lo[0]]) return true;
@@ -325,18 +323,20 @@ __device__ inline bool phAnyCandidate(const DScene& S, D3 p) {
 __global__ void __launch_bounds__(128) k_photon_gather(const __grid_constant__ DScene S, long long n, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, Counters* ctr) {
   __shared__ PhWarpShared shw[4];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; const unsigned lane = threadIdx.x & 31;
-  bool needs = false; D3 loc = d3(0, 0, 0); int shIdx = -1;
-  if (i < n) { const SurfRec s = surf[i]; if (s.valid) { shIdx = s.shader; const FShader& sh = S.shaders[shIdx];
-      needs = !(sh.flags & SF_SIMPLE) && (sh.KRefl == 0.0) && (sh.flags & SF_USE_PHOTON); loc = d3(s.loc[0], s.loc[1], s.loc[2]); 
-#if DRT_PH_PRECHECK
-      needs = needs && phAnyCandidate(S, loc);
-#endif
+  bool needs = false; D3 loc = d3(0, 0, 0); int shIdx = -1; int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  if (i < n && S.numPhotons > 0) { const SurfRec s = surf[i]; if (s.valid) { shIdx = s.shader; const FShader& sh = S.shaders[shIdx];
+      needs = !(sh.flags & SF_SIMPLE) && (sh.KRefl == 0.0) && (sh.flags & SF_USE_PHOTON); loc = d3(s.loc[0], s.loc[1], s.loc[2]);
+      // every lane prepares ITS query (cell range + empty-neighbourhood test) in parallel; only the candidate scan is warp-serial
+      if (needs) needs = phCellRange(S, loc, lo, hi) && phAnyCandidate(S, lo, hi);
     } }
   unsigned mask = __ballot_sync(0xffffffffu, needs);
   while (mask) {
     const int src = __ffs(mask) - 1; mask &= mask - 1;
     D3 p = d3(__shfl_sync(0xffffffffu, loc.x, src), __shfl_sync(0xffffffffu, loc.y, src), __shfl_sync(0xffffffffu, loc.z, src));
-    double sum[3], dmax2; phWarpGather(S, p, shw[threadIdx.x >> 5], sum, dmax2, nullptr);
+    int qlo[3], qhi[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { qlo[k] = __shfl_sync(0xffffffffu, lo[k], src); qhi[k] = __shfl_sync(0xffffffffu, hi[k], src); }
+    double sum[3], dmax2; phWarpGather(S, p, qlo, qhi, shw[threadIdx.x >> 5], sum, dmax2, nullptr);
     if ((int)lane == src && dmax2 > 0) {
       const double area = DRT_PI_F * dmax2; const D3 irr = d3(sum[0] / area, sum[1] / area, sum[2] / area); const FShader& sh = S.shaders[shIdx];
       double* l = nodes[i].local;
@@ -352,7 +352,8 @@ __global__ void __launch_bounds__(128) k_photon_gather(const __grid_constant__ D
 __global__ void __launch_bounds__(128) k_photon_probe(const __grid_constant__ DScene S, long long n, const double* __restrict__ pts, double* __restrict__ out) {
   __shared__ PhWarpShared shw[4];
   const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; if (q >= n) return;
-  double sum[3], dmax2; unsigned long long vis = 0; phWarpGather(S, d3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]), shw[threadIdx.x >> 5], sum, dmax2, &vis);
+  double sum[3] = {0, 0, 0}, dmax2 = 0; unsigned long long vis = 0; int lo[3], hi[3]; const D3 p = d3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]);
+  if (phCellRange(S, p, lo, hi)) phWarpGather(S, p, lo, hi, shw[threadIdx.x >> 5], sum, dmax2, &vis);
   if ((threadIdx.x & 31) == 0) { out[5 * q] = sum[0]; out[5 * q + 1] = sum[1]; out[5 * q + 2] = sum[2]; out[5 * q + 3] = dmax2; out[5 * q + 4] = (double)vis; }
 }
 
