@@ -128,12 +128,20 @@ def main():
     ap.add_argument("--accel", type=int, default=int(os.environ.get("DRT_ACCEL", "1")), help="0 reference-topology literal order, 1 reference-topology near-first (bit-identical results, default), 2 GPU LBVH")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="bun69k", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="bun69k", choices=sorted(WORKLOADS) + ["synth"])
+    ap.add_argument("--synth", default="soup:65536", help="with --workload synth: soup:N (N random triangles) or grid:K (K^3 bunny instances), see tools/make_synth.py")
     ap.add_argument("--photons", type=int, default=None, help="photons cast per light for the photon workloads (sweep 1M..64M)")
     ap.add_argument("--res", default=None, help="COLSxROWS override")
     ap.add_argument("--spp", type=int, default=None)
     args = ap.parse_args()
     global METRIC
+    if args.workload == "synth":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import make_synth
+        kind, n = args.synth.split(":")
+        path = getattr(make_synth, kind)(int(n)) if int(os.environ.get("RANK", "0")) == 0 or not os.path.exists(os.path.join(make_synth.GEN, "%s_%s.cli" % (kind, n))) else os.path.join(make_synth.GEN, "%s_%s.cli" % (kind, n))
+        WORKLOADS["synth"] = dict(scene="gen/" + os.path.basename(path), cols=3840, rows=2160, spp=16, photons=-1, metric="Mrays/s (all ray types), synthetic %s 4K 16spp" % args.synth,
+                                  desc="SURVEY 8(d) synthetic scaling scene %s under the config-2 camera and lights" % args.synth)
     WORKLOAD.clear(); WORKLOAD.update(WORKLOADS[args.workload]); METRIC = WORKLOAD["metric"]
     if args.photons is not None and WORKLOAD["photons"] >= 0:
         WORKLOAD["photons"] = args.photons
@@ -275,7 +283,7 @@ def main():
                 "config": {"workload": "%s %dx%d %dspp%s (%s)" % (w["scene"], w["cols"], w["rows"], w["spp"], (", %d photons cast per light" % w["photons"]) if has_photons else "", w["desc"]),
                            "accel": ["reference-topology literal", "reference-topology fast", "lbvh"][args.accel], "l2": "flushed between timed iterations (256 MiB fill)", "partition": "interleaved 8-row chunks" if world > 1 else "single GPU",
                            "rays_per_frame": rays},
-                "frame_ms": round(ms_per_step, 3), "frame_crc32": frame_crc, "stages_ms_rank0_last_step": {k: round(v, 3) for k, v in stage.items()}, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
+                "frame_ms": round(ms_per_step, 3), "frame_crc32": frame_crc, "accel_info": scene.accel_info(), "stages_ms_rank0_last_step": {k: round(v, 3) for k, v in stage.items()}, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()

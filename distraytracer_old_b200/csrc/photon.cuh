@@ -198,8 +198,8 @@ struct PhWarpShared { uint32_t hist[DRT_PH_BINS]; double listD2[DRT_PH_LIST]; ui
 // finished exactly (double d^2, index tie-break) on the short list of the boundary bin.
 // cells the bounding cube of the search sphere overlaps (radius inflated by 1e-7 so that no photon with d^2 < r^2 can sit in a cell outside
 // the range whatever the rounding of its own cell index); false when the cube misses the grid
-__device__ __forceinline__ bool phCellRange(const DScene& S, D3 p, int lo[3], int hi[3]) {
-  const double rr = sqrt(S.g.phMaxDist2) * 1.0000001, cell = S.cellSize; const double pp[3] = {p.x, p.y, p.z}; bool ok = true;
+__device__ __forceinline__ bool phCellRange(const DScene& S, D3 p, double radius2, int lo[3], int hi[3]) {
+  const double rr = sqrt(radius2) * 1.0000001, cell = S.cellSize; const double pp[3] = {p.x, p.y, p.z}; bool ok = true;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const double a = floor((pp[k] - rr - S.gridMin[k]) / cell), b = floor((pp[k] + rr - S.gridMin[k]) / cell); const int dim = (int)S.gridDim[k];
@@ -208,10 +208,11 @@ __device__ __forceinline__ bool phCellRange(const DScene& S, D3 p, int lo[3], in
   }
   return ok;
 }
-__device__ inline void phWarpGather(const DScene& S, D3 p, const int lo[3], const int hi[3], PhWarpShared& sh, double sum[3], double& dmax2, unsigned long long* visited) {
-  const unsigned lane = threadIdx.x & 31; const double r2 = S.g.phMaxDist2; const int K = S.g.kNhood;
+// r2: search threshold (the scene's r^2, or a smaller guess -- then `needAll`: return false without a result if fewer than k photons are inside it)
+__device__ inline bool phWarpGather(const DScene& S, D3 p, double r2, bool needAll, const int lo[3], const int hi[3], PhWarpShared& sh, double sum[3], double& dmax2, unsigned long long* visited) {
+  const unsigned lane = threadIdx.x & 31; const int K = S.g.kNhood;
   sum[0] = sum[1] = sum[2] = 0; dmax2 = 0;
-  if (S.numPhotons == 0 || K <= 0) return;
+  if (S.numPhotons == 0 || K <= 0) return true;
   const double cell = S.cellSize; (void)cell;
   const double qscale = 4294967295.0 / r2;          // quantised key: monotone non-decreasing in d^2, < 2^32 for d^2 < r^2
   const double4* __restrict__ P = reinterpret_cast<const double4*>(S.phPos); const double4* __restrict__ W = reinterpret_cast<const double4*>(S.phPwr);
@@ -258,6 +259,7 @@ __device__ inline void phWarpGather(const DScene& S, D3 p, const int lo[3], cons
     });
     if (visited && shift == 32 && lane == 0) *visited += vis;
     __syncwarp();
+    if (needAll && shift == 32 && (int)m < need) return false;              // the guessed radius holds fewer than k photons: caller retries with the full one
     if ((int)m <= need) { takeAllUndecided = true; break; }                 // fewer undecided candidates than still needed: all of them are in
     // find the bin where the running count reaches `need`
     uint32_t loc[8], s = 0;
@@ -308,35 +310,56 @@ __device__ inline void phWarpGather(const DScene& S, D3 p, const int lo[3], cons
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
   sum[0] = s0; sum[1] = s1; sum[2] = s2; dmax2 = mx;
+  return true;
 }
 
 // cheap per-lane test: does any cell the search sphere's bounding cube overlaps hold a photon at all?  (sparse caustic maps: most queries do not)
-__device__ inline bool phAnyCandidate(const DScene& S, const int lo[3], const int hi[3]) {
+__device__ inline uint32_t phCountCandidates(const DScene& S, const int lo[3], const int hi[3]) {
+  uint32_t c = 0;
   for (int cz = lo[2]; cz <= hi[2]; ++cz) for (int cy = lo[1]; cy <= hi[1]; ++cy) {
     const uint32_t row = ((uint32_t)cz * S.gridDim[1] + (uint32_t)cy) * S.gridDim[0];
-    if (S.cellStart[row + hi[0] + 1] > S.cellStart[row + lo[0]]) return true;
+    c += S.cellStart[row + hi[0] + 1] - S.cellStart[row + lo[0]];
   }
-  return false;
+  return c;
+}
+// Dense neighbourhoods: the k-th neighbour is far closer than r, so most of the r-sphere's candidates are wasted work.  Guess a radius that
+// should hold ~4k photons (photons lie on surfaces: count ~ area), search that first and fall back to r only if it holds fewer than k.
+// Exact either way: if >= k photons have d^2 < guess, the k nearest are among them and every such photon sits in the guess sphere's cells.
+__device__ __forceinline__ double phGuessRadius2(const DScene& S, uint32_t count, const int lo[3], const int hi[3]) {
+  const double r2 = S.g.phMaxDist2; const int K = S.g.kNhood;
+  if (count < (uint32_t)(16 * K)) return r2;
+  const int ex = hi[0] - lo[0] + 1, ey = hi[1] - lo[1] + 1, ez = hi[2] - lo[2] + 1; const int e = ex > ey ? (ex > ez ? ex : ez) : (ey > ez ? ey : ez);
+  const double side = e * S.cellSize, g2 = (4.0 * K) * side * side / (DRT_PI * (double)count);
+  return g2 < 0.5 * r2 ? g2 : r2;
 }
 // One warp serves the 32 surface records it owns, one query at a time. Runs between k_shade (local = ambient) and k_light
 // (local += direct), which is the reference's accumulation order (myObjShader.java:413-425).
 __global__ void __launch_bounds__(128) k_photon_gather(const __grid_constant__ DScene S, long long n, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, Counters* ctr) {
   __shared__ PhWarpShared shw[4];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; const unsigned lane = threadIdx.x & 31;
-  bool needs = false; D3 loc = d3(0, 0, 0); int shIdx = -1; int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  bool needs = false; D3 loc = d3(0, 0, 0); int shIdx = -1; int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, glo[3] = {0, 0, 0}, ghi[3] = {0, 0, 0}; double g2 = S.g.phMaxDist2;
   if (i < n && S.numPhotons > 0) { const SurfRec s = surf[i]; if (s.valid) { shIdx = s.shader; const FShader& sh = S.shaders[shIdx];
       needs = !(sh.flags & SF_SIMPLE) && (sh.KRefl == 0.0) && (sh.flags & SF_USE_PHOTON); loc = d3(s.loc[0], s.loc[1], s.loc[2]);
-      // every lane prepares ITS query (cell range + empty-neighbourhood test) in parallel; only the candidate scan is warp-serial
-      if (needs) needs = phCellRange(S, loc, lo, hi) && phAnyCandidate(S, lo, hi);
+      // every lane prepares ITS query (cell range, candidate count, radius guess) in parallel; only the candidate scan is warp-serial
+      if (needs) { needs = phCellRange(S, loc, S.g.phMaxDist2, lo, hi); uint32_t cnt = needs ? phCountCandidates(S, lo, hi) : 0u; needs = cnt > 0;
+        if (needs) { g2 = phGuessRadius2(S, cnt, lo, hi); if (g2 < S.g.phMaxDist2) { if (!phCellRange(S, loc, g2, glo, ghi)) g2 = S.g.phMaxDist2; } } }
     } }
   unsigned mask = __ballot_sync(0xffffffffu, needs);
   while (mask) {
     const int src = __ffs(mask) - 1; mask &= mask - 1;
     D3 p = d3(__shfl_sync(0xffffffffu, loc.x, src), __shfl_sync(0xffffffffu, loc.y, src), __shfl_sync(0xffffffffu, loc.z, src));
-    int qlo[3], qhi[3];
+    const double qg2 = __shfl_sync(0xffffffffu, g2, src);
+    int qlo[3], qhi[3]; double sum[3], dmax2; bool done = false;
+    if (qg2 < S.g.phMaxDist2) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { qlo[k] = __shfl_sync(0xffffffffu, lo[k], src); qhi[k] = __shfl_sync(0xffffffffu, hi[k], src); }
-    double sum[3], dmax2; phWarpGather(S, p, qlo, qhi, shw[threadIdx.x >> 5], sum, dmax2, nullptr);
+      for (int k = 0; k < 3; ++k) { qlo[k] = __shfl_sync(0xffffffffu, glo[k], src); qhi[k] = __shfl_sync(0xffffffffu, ghi[k], src); }
+      done = phWarpGather(S, p, qg2, true, qlo, qhi, shw[threadIdx.x >> 5], sum, dmax2, nullptr);
+    }
+    if (!done) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { qlo[k] = __shfl_sync(0xffffffffu, lo[k], src); qhi[k] = __shfl_sync(0xffffffffu, hi[k], src); }
+      phWarpGather(S, p, S.g.phMaxDist2, false, qlo, qhi, shw[threadIdx.x >> 5], sum, dmax2, nullptr);
+    }
     if ((int)lane == src && dmax2 > 0) {
       const double area = DRT_PI_F * dmax2; const D3 irr = d3(sum[0] / area, sum[1] / area, sum[2] / area); const FShader& sh = S.shaders[shIdx];
       double* l = nodes[i].local;
@@ -353,7 +376,11 @@ __global__ void __launch_bounds__(128) k_photon_probe(const __grid_constant__ DS
   __shared__ PhWarpShared shw[4];
   const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; if (q >= n) return;
   double sum[3] = {0, 0, 0}, dmax2 = 0; unsigned long long vis = 0; int lo[3], hi[3]; const D3 p = d3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]);
-  if (phCellRange(S, p, lo, hi)) phWarpGather(S, p, lo, hi, shw[threadIdx.x >> 5], sum, dmax2, &vis);
+  if (phCellRange(S, p, S.g.phMaxDist2, lo, hi)) {      // same two-step search as k_photon_gather
+    const uint32_t cnt = phCountCandidates(S, lo, hi); const double g2 = phGuessRadius2(S, cnt, lo, hi); int glo[3], ghi[3]; bool done = false;
+    if (cnt > 0 && g2 < S.g.phMaxDist2 && phCellRange(S, p, g2, glo, ghi)) done = phWarpGather(S, p, g2, true, glo, ghi, shw[threadIdx.x >> 5], sum, dmax2, &vis);
+    if (cnt > 0 && !done) phWarpGather(S, p, S.g.phMaxDist2, false, lo, hi, shw[threadIdx.x >> 5], sum, dmax2, &vis);
+  }
   if ((threadIdx.x & 31) == 0) { out[5 * q] = sum[0]; out[5 * q + 1] = sum[1]; out[5 * q + 2] = sum[2]; out[5 * q + 3] = dmax2; out[5 * q + 4] = (double)vis; }
 }
 
