@@ -171,8 +171,12 @@ __device__ __forceinline__ int phCellCoord(double v, double gmin, double cell, i
 __global__ void k_photon_cellkeys(const PhotonRec* __restrict__ rec, long long n, PhGrid G, uint32_t* __restrict__ keys, uint32_t* __restrict__ cellCount) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
   const PhotonRec r = rec[i];
-  uint32_t cx = phCellCoord(r.x, G.gmin[0], G.cell, G.dim[0]), cy = phCellCoord(r.y, G.gmin[1], G.cell, G.dim[1]), cz = phCellCoord(r.z, G.gmin[2], G.cell, G.dim[2]);
-  uint32_t key = (cz * G.dim[1] + cy) * G.dim[0] + cx; keys[i] = key; atomicAdd(&cellCount[key], 1u);
+  // two-level key: coarse cell (side = search radius, x fastest: a run of coarse cells along x is one contiguous photon range) and, inside it,
+  // a 4x4x4 fine sub-cell index.  Every coordinate derives from the FINE one, so both levels are consistent with each other.
+  const double cf = G.cell * 0.25;
+  const uint32_t fx = phCellCoord(r.x, G.gmin[0], cf, 4 * G.dim[0]), fy = phCellCoord(r.y, G.gmin[1], cf, 4 * G.dim[1]), fz = phCellCoord(r.z, G.gmin[2], cf, 4 * G.dim[2]);
+  const uint32_t key = ((((fz >> 2) * G.dim[1] + (fy >> 2)) * G.dim[0] + (fx >> 2)) << 6) | ((fz & 3u) << 4) | ((fy & 3u) << 2) | (fx & 3u);
+  keys[i] = key; atomicAdd(&cellCount[key], 1u);
 }
 // sorted order -> the two 32-byte-per-photon arrays the gather reads with 128-bit loads
 __global__ void k_photon_reorder(const PhotonRec* __restrict__ rec, const uint32_t* __restrict__ order, long long n, double4* __restrict__ pos, double4* __restrict__ pwr) {
@@ -209,45 +213,44 @@ __device__ __forceinline__ bool phCellRange(const DScene& S, D3 p, double radius
   return ok;
 }
 // r2: search threshold (the scene's r^2, or a smaller guess -- then `needAll`: return false without a result if fewer than k photons are inside it)
-__device__ inline bool phWarpGather(const DScene& S, D3 p, double r2, bool needAll, const int lo[3], const int hi[3], PhWarpShared& sh, double sum[3], double& dmax2, unsigned long long* visited) {
+__device__ inline bool phWarpGather(const DScene& S, D3 p, double r2, bool needAll, bool atMostK, int fineHalf, const int lo[3], const int hi[3], PhWarpShared& sh, double sum[3], double& dmax2, unsigned long long* visited) {
   const unsigned lane = threadIdx.x & 31; const int K = S.g.kNhood;
   sum[0] = sum[1] = sum[2] = 0; dmax2 = 0;
   if (S.numPhotons == 0 || K <= 0) return true;
-  const double cell = S.cellSize; (void)cell;
   const double qscale = 4294967295.0 / r2;          // quantised key: monotone non-decreasing in d^2, < 2^32 for d^2 < r^2
   const double4* __restrict__ P = reinterpret_cast<const double4*>(S.phPos); const double4* __restrict__ W = reinterpret_cast<const double4*>(S.phPwr);
-  // visit every candidate of the <= 3x3 rows of cells that the search sphere can reach; F(j, d2, q, ok) is called warp-wide, ok = d2 < r2.
-  // A row (cy, cz) is skipped when the sphere misses its y/z slab, and its x range is cut to the chord of the sphere at that distance
-  // (slab edges padded by 1e-9 cell: the cell index of a photon is a rounded quotient).
-  const double rr2 = r2 * 1.0000003, pad = 1e-9 * cell; (void)rr2; (void)pad;
+  // visit every candidate; F(j, d2, q, ok) is called warp-wide, ok = d2 < r2.  Two shapes of candidate set:
+  //   coarse (fineHalf < 0): the <= 3x3 rows of coarse cells lo..hi the r-sphere's bounding cube overlaps, one contiguous photon range per row
+  //   fine   (fineHalf = s): the (2s+1)^3 fine sub-cells around the fine cell lo[] that contains p (every photon within s fine cells of p)
+  auto scan = [&](uint32_t a, uint32_t b, auto&& F) {
+    for (uint32_t j0 = a; j0 < b; j0 += 32) {
+      const uint32_t j = j0 + lane; bool ok = j < b; double d2 = 0;
+      if (ok) { const double4 q = P[j]; const double dx = p.x - q.x, dy2 = p.y - q.y, dz2 = p.z - q.z; d2 = dx * dx + dy2 * dy2 + dz2 * dz2; ok = d2 < r2; }
+      F(j, d2, ok ? (uint32_t)(d2 * qscale) : 0u, ok);
+    }
+  };
   auto forEach = [&](auto&& F) {
-    for (int cz = lo[2]; cz <= hi[2]; ++cz) {
-      const double z0 = S.gridMin[2] + cz * cell, dz = fmax(0.0, fmax(z0 - pad - p.z, p.z - (z0 + cell + pad)));
-      for (int cy = lo[1]; cy <= hi[1]; ++cy) {
-        const double y0 = S.gridMin[1] + cy * cell, dy = fmax(0.0, fmax(y0 - pad - p.y, p.y - (y0 + cell + pad)));
-#if DRT_PH_CULL
-        const double rem2 = rr2 - dy * dy - dz * dz;
-        if (rem2 < 0) continue;
-        const double xr = sqrt(rem2) + pad;
-        int x0 = (int)floor((p.x - xr - S.gridMin[0]) / cell), x1 = (int)floor((p.x + xr - S.gridMin[0]) / cell);
-        x0 = x0 < lo[0] ? lo[0] : x0; x1 = x1 > hi[0] ? hi[0] : x1;
-        if (x1 < x0) continue;
-#else
-        (void)dy; (void)dz; const int x0 = lo[0], x1 = hi[0];
-#endif
+    if (fineHalf < 0) {
+      for (int cz = lo[2]; cz <= hi[2]; ++cz) for (int cy = lo[1]; cy <= hi[1]; ++cy) {
         const uint32_t row = ((uint32_t)cz * S.gridDim[1] + (uint32_t)cy) * S.gridDim[0];
-        const uint32_t a = S.cellStart[row + x0], b = S.cellStart[row + x1 + 1];
-        for (uint32_t j0 = a; j0 < b; j0 += 32) {
-          const uint32_t j = j0 + lane; bool ok = j < b; double d2 = 0;
-          if (ok) { const double4 q = P[j]; const double dx = p.x - q.x, dy2 = p.y - q.y, dz2 = p.z - q.z; d2 = dx * dx + dy2 * dy2 + dz2 * dz2; ok = d2 < r2; }
-          F(j, d2, ok ? (uint32_t)(d2 * qscale) : 0u, ok);
+        scan(S.cellStart[(size_t)(row + lo[0]) << 6], S.cellStart[(size_t)(row + hi[0] + 1) << 6], F);
+      }
+    } else {
+      const int fdx = 4 * (int)S.gridDim[0], fdy = 4 * (int)S.gridDim[1], fdz = 4 * (int)S.gridDim[2];
+      const int z0 = max(lo[2] - fineHalf, 0), z1 = min(lo[2] + fineHalf, fdz - 1), y0 = max(lo[1] - fineHalf, 0), y1 = min(lo[1] + fineHalf, fdy - 1), x0 = max(lo[0] - fineHalf, 0), x1 = min(lo[0] + fineHalf, fdx - 1);
+      for (int fz = z0; fz <= z1; ++fz) for (int fy = y0; fy <= y1; ++fy) {
+        const uint32_t crow = ((uint32_t)(fz >> 2) * S.gridDim[1] + (uint32_t)(fy >> 2)) * S.gridDim[0], sub = ((uint32_t)(fz & 3) << 4) | ((uint32_t)(fy & 3) << 2);
+        for (int fx = x0; fx <= x1; ) {          // fine cells of one coarse cell that share (fy, fz) are consecutive keys: one range per run
+          const int runEnd = min(x1, fx | 3); const size_t k0 = ((size_t)(crow + (uint32_t)(fx >> 2)) << 6) | sub | (uint32_t)(fx & 3);
+          scan(S.cellStart[k0], S.cellStart[k0 + (size_t)(runEnd - fx) + 1], F);
+          fx = runEnd + 1;
         }
       }
     }
   };
   // level loop: keys with (q >> shift) < prefix are already known to be inside; those == prefix are undecided
-  uint32_t prefix = 0; int shift = 32; int need = K; bool takeAllUndecided = false, haveList = false;
-  while (true) {
+  uint32_t prefix = 0; int shift = 32; int need = K; bool takeAllUndecided = atMostK, haveList = false;     // atMostK: the candidate cells hold <= k photons, nothing to select
+  while (!atMostK) {
     const int nshift = shift - 8;
     for (int i = lane; i < DRT_PH_BINS; i += 32) sh.hist[i] = 0;
     __syncwarp();
@@ -318,47 +321,65 @@ __device__ inline uint32_t phCountCandidates(const DScene& S, const int lo[3], c
   uint32_t c = 0;
   for (int cz = lo[2]; cz <= hi[2]; ++cz) for (int cy = lo[1]; cy <= hi[1]; ++cy) {
     const uint32_t row = ((uint32_t)cz * S.gridDim[1] + (uint32_t)cy) * S.gridDim[0];
-    c += S.cellStart[row + hi[0] + 1] - S.cellStart[row + lo[0]];
+    c += S.cellStart[(size_t)(row + hi[0] + 1) << 6] - S.cellStart[(size_t)(row + lo[0]) << 6];
   }
   return c;
 }
-// Dense neighbourhoods: the k-th neighbour is far closer than r, so most of the r-sphere's candidates are wasted work.  Guess a radius that
-// should hold ~4k photons (photons lie on surfaces: count ~ area), search that first and fall back to r only if it holds fewer than k.
-// Exact either way: if >= k photons have d^2 < guess, the k nearest are among them and every such photon sits in the guess sphere's cells.
-__device__ __forceinline__ double phGuessRadius2(const DScene& S, uint32_t count, const int lo[3], const int hi[3]) {
-  const double r2 = S.g.phMaxDist2; const int K = S.g.kNhood;
-  if (count < (uint32_t)(16 * K)) return r2;
-  const int ex = hi[0] - lo[0] + 1, ey = hi[1] - lo[1] + 1, ez = hi[2] - lo[2] + 1; const int e = ex > ey ? (ex > ez ? ex : ez) : (ey > ez ? ey : ez);
-  const double side = e * S.cellSize, g2 = (4.0 * K) * side * side / (DRT_PI * (double)count);
-  return g2 < 0.5 * r2 ? g2 : r2;
+// Dense neighbourhoods: the k-th neighbour is far closer than r, so most of the r-sphere's candidates are wasted work.  Per query (lane-parallel):
+//   count the photons in the fine cube of half-width 1, then 2, around p's fine cell; the first one that holds >= 4k photons gives the plan
+//   "search radius s * fineCell over that cube" -- exact if >= k photons turn out to lie inside that radius (every photon closer than s fine
+//   cells to p is in the cube), otherwise the caller falls back to the full radius over the coarse rows.
+struct PhPlan { int fineHalf; int c[3]; int h[3]; double r2; };      // fineHalf < 0: coarse rows c..h with threshold r2
+__device__ __forceinline__ uint32_t phCountFineCube(const DScene& S, const int f[3], int s) {
+  const int fdx = 4 * (int)S.gridDim[0], fdy = 4 * (int)S.gridDim[1], fdz = 4 * (int)S.gridDim[2];
+  const int z0 = max(f[2] - s, 0), z1 = min(f[2] + s, fdz - 1), y0 = max(f[1] - s, 0), y1 = min(f[1] + s, fdy - 1), x0 = max(f[0] - s, 0), x1 = min(f[0] + s, fdx - 1);
+  uint32_t c = 0;
+  for (int fz = z0; fz <= z1; ++fz) for (int fy = y0; fy <= y1; ++fy) {
+    const uint32_t crow = ((uint32_t)(fz >> 2) * S.gridDim[1] + (uint32_t)(fy >> 2)) * S.gridDim[0], sub = ((uint32_t)(fz & 3) << 4) | ((uint32_t)(fy & 3) << 2);
+    for (int fx = x0; fx <= x1; ) { const int runEnd = min(x1, fx | 3); const size_t k0 = ((size_t)(crow + (uint32_t)(fx >> 2)) << 6) | sub | (uint32_t)(fx & 3);
+      c += S.cellStart[k0 + (size_t)(runEnd - fx) + 1] - S.cellStart[k0]; fx = runEnd + 1; }
+  }
+  return c;
+}
+__device__ __forceinline__ void phMakePlan(const DScene& S, D3 p, uint32_t coarseCount, const int lo[3], const int hi[3], PhPlan& pl) {
+  const int K = S.g.kNhood; pl.fineHalf = -1; pl.r2 = S.g.phMaxDist2;
+  for (int k = 0; k < 3; ++k) { pl.c[k] = lo[k]; pl.h[k] = hi[k]; }
+  if (coarseCount < (uint32_t)(8 * K)) return;
+  const double cf = S.cellSize * 0.25, pp[3] = {p.x, p.y, p.z}; int f[3]; bool inside = true;
+  for (int k = 0; k < 3; ++k) { const double a = floor((pp[k] - S.gridMin[k]) / cf); const int fd = 4 * (int)S.gridDim[k]; if (!(a >= 0) || !(a <= fd - 1)) inside = false; f[k] = (int)a; }
+  if (!inside) return;
+  for (int s = 1; s <= 2; ++s) if (phCountFineCube(S, f, s) >= (uint32_t)(4 * K)) {
+    pl.fineHalf = s; for (int k = 0; k < 3; ++k) { pl.c[k] = f[k]; pl.h[k] = s; }
+    const double rad = s * cf * (1.0 - 1e-6); pl.r2 = rad * rad; return;       // 1e-6: a photon's own fine index is a rounded quotient
+  }
 }
 // One warp serves the 32 surface records it owns, one query at a time. Runs between k_shade (local = ambient) and k_light
 // (local += direct), which is the reference's accumulation order (myObjShader.java:413-425).
 __global__ void __launch_bounds__(128) k_photon_gather(const __grid_constant__ DScene S, long long n, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, Counters* ctr) {
   __shared__ PhWarpShared shw[4];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; const unsigned lane = threadIdx.x & 31;
-  bool needs = false; D3 loc = d3(0, 0, 0); int shIdx = -1; int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, glo[3] = {0, 0, 0}, ghi[3] = {0, 0, 0}; double g2 = S.g.phMaxDist2;
+  bool needs = false, few = false; D3 loc = d3(0, 0, 0); int shIdx = -1; int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; PhPlan pl; pl.fineHalf = -1; pl.r2 = S.g.phMaxDist2; for (int k = 0; k < 3; ++k) pl.c[k] = pl.h[k] = 0;
   if (i < n && S.numPhotons > 0) { const SurfRec s = surf[i]; if (s.valid) { shIdx = s.shader; const FShader& sh = S.shaders[shIdx];
       needs = !(sh.flags & SF_SIMPLE) && (sh.KRefl == 0.0) && (sh.flags & SF_USE_PHOTON); loc = d3(s.loc[0], s.loc[1], s.loc[2]);
-      // every lane prepares ITS query (cell range, candidate count, radius guess) in parallel; only the candidate scan is warp-serial
-      if (needs) { needs = phCellRange(S, loc, S.g.phMaxDist2, lo, hi); uint32_t cnt = needs ? phCountCandidates(S, lo, hi) : 0u; needs = cnt > 0;
-        if (needs) { g2 = phGuessRadius2(S, cnt, lo, hi); if (g2 < S.g.phMaxDist2) { if (!phCellRange(S, loc, g2, glo, ghi)) g2 = S.g.phMaxDist2; } } }
+      // every lane prepares ITS query (cell range, candidate counts, search plan) in parallel; only the candidate scan is warp-serial
+      if (needs) { needs = phCellRange(S, loc, S.g.phMaxDist2, lo, hi); const uint32_t cnt = needs ? phCountCandidates(S, lo, hi) : 0u; needs = cnt > 0; few = cnt <= (uint32_t)S.g.kNhood; if (needs) phMakePlan(S, loc, cnt, lo, hi, pl); }
     } }
   unsigned mask = __ballot_sync(0xffffffffu, needs);
   while (mask) {
     const int src = __ffs(mask) - 1; mask &= mask - 1;
     D3 p = d3(__shfl_sync(0xffffffffu, loc.x, src), __shfl_sync(0xffffffffu, loc.y, src), __shfl_sync(0xffffffffu, loc.z, src));
-    const double qg2 = __shfl_sync(0xffffffffu, g2, src);
+    const int fineHalf = __shfl_sync(0xffffffffu, pl.fineHalf, src);
     int qlo[3], qhi[3]; double sum[3], dmax2; bool done = false;
-    if (qg2 < S.g.phMaxDist2) {
+    if (fineHalf > 0) {
+      const double pr2 = __shfl_sync(0xffffffffu, pl.r2, src);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { qlo[k] = __shfl_sync(0xffffffffu, glo[k], src); qhi[k] = __shfl_sync(0xffffffffu, ghi[k], src); }
-      done = phWarpGather(S, p, qg2, true, qlo, qhi, shw[threadIdx.x >> 5], sum, dmax2, nullptr);
+      for (int k = 0; k < 3; ++k) { qlo[k] = __shfl_sync(0xffffffffu, pl.c[k], src); qhi[k] = fineHalf; }
+      done = phWarpGather(S, p, pr2, true, false, fineHalf, qlo, qhi, shw[threadIdx.x >> 5], sum, dmax2, nullptr);
     }
     if (!done) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) { qlo[k] = __shfl_sync(0xffffffffu, lo[k], src); qhi[k] = __shfl_sync(0xffffffffu, hi[k], src); }
-      phWarpGather(S, p, S.g.phMaxDist2, false, qlo, qhi, shw[threadIdx.x >> 5], sum, dmax2, nullptr);
+      phWarpGather(S, p, S.g.phMaxDist2, false, __shfl_sync(0xffffffffu, (int)few, src) != 0, -1, qlo, qhi, shw[threadIdx.x >> 5], sum, dmax2, nullptr);
     }
     if ((int)lane == src && dmax2 > 0) {
       const double area = DRT_PI_F * dmax2; const D3 irr = d3(sum[0] / area, sum[1] / area, sum[2] / area); const FShader& sh = S.shaders[shIdx];
@@ -377,9 +398,10 @@ __global__ void __launch_bounds__(128) k_photon_probe(const __grid_constant__ DS
   const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; if (q >= n) return;
   double sum[3] = {0, 0, 0}, dmax2 = 0; unsigned long long vis = 0; int lo[3], hi[3]; const D3 p = d3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]);
   if (phCellRange(S, p, S.g.phMaxDist2, lo, hi)) {      // same two-step search as k_photon_gather
-    const uint32_t cnt = phCountCandidates(S, lo, hi); const double g2 = phGuessRadius2(S, cnt, lo, hi); int glo[3], ghi[3]; bool done = false;
-    if (cnt > 0 && g2 < S.g.phMaxDist2 && phCellRange(S, p, g2, glo, ghi)) done = phWarpGather(S, p, g2, true, glo, ghi, shw[threadIdx.x >> 5], sum, dmax2, &vis);
-    if (cnt > 0 && !done) phWarpGather(S, p, S.g.phMaxDist2, false, lo, hi, shw[threadIdx.x >> 5], sum, dmax2, &vis);
+    const uint32_t cnt = phCountCandidates(S, lo, hi); bool done = false;
+    if (cnt > 0) { PhPlan pl; phMakePlan(S, p, cnt, lo, hi, pl);
+      if (pl.fineHalf > 0) done = phWarpGather(S, p, pl.r2, true, false, pl.fineHalf, pl.c, pl.h, shw[threadIdx.x >> 5], sum, dmax2, &vis);
+      if (!done) phWarpGather(S, p, S.g.phMaxDist2, false, cnt <= (uint32_t)S.g.kNhood, -1, lo, hi, shw[threadIdx.x >> 5], sum, dmax2, &vis); }
   }
   if ((threadIdx.x & 31) == 0) { out[5 * q] = sum[0]; out[5 * q + 1] = sum[1]; out[5 * q + 2] = sum[2]; out[5 * q + 3] = dmax2; out[5 * q + 4] = (double)vis; }
 }
@@ -457,10 +479,10 @@ struct PhotonMap {
     PhGrid G;
     while (true) {
       double cells = 1; for (int k = 0; k < 3; ++k) { double d = std::floor((mx[k] - mn[k]) / cell) + 1; if (d < 1) d = 1; G.dim[k] = (uint32_t)std::min(d, 4.0e9); cells *= d; }
-      if (cells <= (double)(1u << 26)) break;
+      if (cells <= (double)(1u << 22)) break;          // x 64 fine sub-cells = at most 2^28 cellStart entries (1 GiB)
       cell *= 2;
     }
-    G.cell = cell; for (int k = 0; k < 3; ++k) G.gmin[k] = mn[k]; G.nCells = G.dim[0] * G.dim[1] * G.dim[2]; grid = G;
+    G.cell = cell; for (int k = 0; k < 3; ++k) G.gmin[k] = mn[k]; G.nCells = G.dim[0] * G.dim[1] * G.dim[2] * 64u; grid = G;     // nCells counts FINE cells
     // keys + per-cell counts, cellStart = exclusive scan (nCells + 1 entries: cellStart[nCells] = n)
     if ((size_t)G.nCells + 1 > cellCap) { cudaFree(cellStart); cellCap = (size_t)G.nCells + 1 + (size_t)G.nCells / 4; CK(cudaMalloc(&cellStart, cellCap * 4)); }
     if ((size_t)n > sortedCap) { cudaFree(pos); cudaFree(pwr); sortedCap = (size_t)n + (size_t)n / 8 + 1024; CK(cudaMalloc(&pos, sortedCap * sizeof(double4))); CK(cudaMalloc(&pwr, sortedCap * sizeof(double4))); }
