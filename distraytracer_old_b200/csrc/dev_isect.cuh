@@ -410,6 +410,15 @@ __device__ __forceinline__ int leanBox(double mnx, double mny, double mnz, doubl
   if (gap > tol) return near_ > 0 ? 1 : 0;
   return (-gap > tol) ? 0 : -1;
 }
+// conventional slab test on the same per-ray ordered planes (LBVH mode: boxes are padded outward, a ray that starts inside enters at t = 0)
+__device__ __forceinline__ int leanBoxStd(double mnx, double mny, double mnz, double mxx, double mxy, double mxz, const LeanRay& R, double& nearOut) {
+  const double nx = ((R.px ? mnx : mxx) - R.ox) * R.ix, fx = ((R.px ? mxx : mnx) - R.ox) * R.ix;
+  const double ny = ((R.py ? mny : mxy) - R.oy) * R.iy, fy = ((R.py ? mxy : mny) - R.oy) * R.iy;
+  const double nz = ((R.pz ? mnz : mxz) - R.oz) * R.iz, fz = ((R.pz ? mxz : mnz) - R.oz) * R.iz;
+  double near_ = nx > ny ? nx : ny; near_ = nz > near_ ? nz : near_; near_ = near_ > 0.0 ? near_ : 0.0;
+  double far_ = fx < fy ? fx : fy; far_ = fz < far_ ? fz : far_;
+  nearOut = near_; return far_ >= near_ ? 1 : 0;
+}
 __device__ __forceinline__ bool regularDir(D3 a) {
   const double x = fabs(a.x), y = fabs(a.y), z = fabs(a.z);
   return x > 1e-100 && x < 1e100 && y > 1e-100 && y < 1e100 && z > 1e-100 && z < 1e100;
@@ -449,7 +458,7 @@ __device__ DRT_LEAN_INLINE bool leanClosest(const DScene& S, const FBvh& B, cons
   R.ix = 1.0 / ax; R.iy = 1.0 / ay; R.iz = 1.0 / az; R.px = ax > 0; R.py = ay > 0; R.pz = az > 0;
   const double tox = ONE_RAY ? R.ox : to.x, toy = ONE_RAY ? R.oy : to.y, toz = ONE_RAY ? R.oz : to.z;
   const double tdx = ONE_RAY ? ax : td.x, tdy = ONE_RAY ? ay : td.y, tdz = ONE_RAY ? az : td.z;
-  FStack stk;
+  FStack stk; const bool stdBox = S.accelMode == 2;
   double bestT = DRT_DMAX; int bestTri = -1, bestRank = 0x7fffffff, bestSt = 0;
   int32_t ref = B.fastRoot;
   while (true) {
@@ -459,7 +468,8 @@ __device__ DRT_LEAN_INLINE bool leanClosest(const DScene& S, const FBvh& B, cons
       const int4 lk = __ldg(reinterpret_cast<const int4*>(q) + 6);
       if (tc) tc->box += 2;
       double teL, teR;
-      const int ql = leanBox(q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, R, teL), qr = leanBox(q3.x, q3.y, q4.x, q4.y, q5.x, q5.y, R, teR);
+      const int ql = stdBox ? leanBoxStd(q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, R, teL) : leanBox(q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, R, teL);
+      const int qr = stdBox ? leanBoxStd(q3.x, q3.y, q4.x, q4.y, q5.x, q5.y, R, teR) : leanBox(q3.x, q3.y, q4.x, q4.y, q5.x, q5.y, R, teR);
       bool hl = ql > 0, hr = qr > 0;
       if (ql >= 0) teL *= 0.999999999999999; else hl = boxExactLB(reinterpret_cast<const double*>(q), R.ox, R.oy, R.oz, ax, ay, az, teL);
       if (qr >= 0) teR *= 0.999999999999999; else hr = boxExactLB(reinterpret_cast<const double*>(q) + 6, R.ox, R.oy, R.oz, ax, ay, az, teR);
@@ -497,10 +507,11 @@ __device__ DRT_LEAN_INLINE bool leanShadow(const DScene& S, const FBvh& B, const
   R.ix = 1.0 / ax; R.iy = 1.0 / ay; R.iz = 1.0 / az; R.px = ax > 0; R.py = ay > 0; R.pz = az > 0;
   const double tox = ONE_RAY ? R.ox : to.x, toy = ONE_RAY ? R.oy : to.y, toz = ONE_RAY ? R.oz : to.z;
   const double tdx = ONE_RAY ? ax : td.x, tdy = ONE_RAY ? ay : td.y, tdz = ONE_RAY ? az : td.z;
-  FStack stk;
+  FStack stk; const bool stdBox = S.accelMode == 2;
   int32_t ref = B.fastRoot;
   auto accept = [&](int q, double te, const double* box6) {       // (dist - entry) > eps, with the exact entry t only when it is too close to call
     if (q == 0) return false;
+    if (stdBox) return (dist - te) > DRT_EPS;
     if (q > 0) { const double diff = dist - te, m = 1e-13 * (fabs(dist) + fabs(te)); if (diff > DRT_EPS + m) return true; if (diff < DRT_EPS - m) return false; }
     double tx; return boxExactLB(box6, R.ox, R.oy, R.oz, ax, ay, az, tx) && (dist - tx) > DRT_EPS;
   };
@@ -511,7 +522,8 @@ __device__ DRT_LEAN_INLINE bool leanShadow(const DScene& S, const FBvh& B, const
       const int4 lk = __ldg(reinterpret_cast<const int4*>(q) + 6);
       if (tc) tc->box += 2;
       double teL, teR;
-      const int ql = leanBox(q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, R, teL), qr = leanBox(q3.x, q3.y, q4.x, q4.y, q5.x, q5.y, R, teR);
+      const int ql = stdBox ? leanBoxStd(q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, R, teL) : leanBox(q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, R, teL);
+      const int qr = stdBox ? leanBoxStd(q3.x, q3.y, q4.x, q4.y, q5.x, q5.y, R, teR) : leanBox(q3.x, q3.y, q4.x, q4.y, q5.x, q5.y, R, teR);
       const bool hl = accept(ql, teL, reinterpret_cast<const double*>(q)), hr = accept(qr, teR, reinterpret_cast<const double*>(q) + 6);
       const int32_t cl = childRef(lk.x, lk.z), cr = childRef(lk.y, lk.w);
       if (hl && hr) { stk.push(cr, 0.f); ref = cl; continue; }
@@ -605,7 +617,7 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
       const Ray r = xfRay(_ray, S.xforms[B.triXform].inv);          // what every leaf child of this mesh would be tested with
       const bool one = sameRay(trans, r);
 #if DRT_LEAN
-      if (S.accelMode == 1 && regularDir(trans.a)) return one ? leanClosest<true>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc) : leanClosest<false>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc);
+      if (regularDir(trans.a)) return one ? leanClosest<true>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc) : leanClosest<false>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc);
 #endif
       return one ? fastClosest<true>(S, B, trans, r, _ray.d, out, tc) : fastClosest<false>(S, B, trans, r, _ray.d, out, tc);
     }
@@ -715,7 +727,7 @@ __device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const
     const Ray r = xfRay(_ray, S.xforms[B.triXform].inv);
     const bool one = sameRay(trans, r);
 #if DRT_LEAN
-    if (S.accelMode == 1 && regularDir(trans.a)) return one ? leanShadow<true>(S, B, trans.o, trans.a, r.o, r.d, dist, tc) : leanShadow<false>(S, B, trans.o, trans.a, r.o, r.d, dist, tc);
+    if (regularDir(trans.a)) return one ? leanShadow<true>(S, B, trans.o, trans.a, r.o, r.d, dist, tc) : leanShadow<false>(S, B, trans.o, trans.a, r.o, r.d, dist, tc);
 #endif
     return one ? fastShadow<true>(S, B, trans, r, dist, tc) : fastShadow<false>(S, B, trans, r, dist, tc);
   }

@@ -405,6 +405,7 @@ void Renderer::upload(const HostScene& hs) {
     FNode* ln = impl_->lbvhNodeBuf.p; FTri* lt = impl_->lbvhTriBuf.p;
     if (n0) CK(cudaMemcpyAsync(ln, d.nodes, n0 * sizeof(FNode), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(lt, d.tris, hs.tris.size() * sizeof(FTri), cudaMemcpyDeviceToDevice, st));
+    { size_t mx = 0; for (const FBvh& B : bv) if (B.fast && B.fastRoot != B.root) mx = std::max(mx, (size_t)B.triCount); impl_->lbvhScratch.ensure(mx); }   // scratch is grow-only and allocated outside the timed build
     CK(cudaEventRecord(impl_->ev[6], st));
     for (const FBvh& B : bv) if (B.fast && B.fastRoot != B.root) {
       const int wrote = lbvhBuild(lt, B.triStart, B.triCount, B.bmin, B.bmax, ln + B.fastRoot, B.fastRoot, impl_->lbvhScratch, st);
