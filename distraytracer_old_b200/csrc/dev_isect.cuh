@@ -118,6 +118,22 @@ __device__ __forceinline__ bool boxAcceptShadow(const double* __restrict__ mn, c
   return boxTestFx(mn, mx, r, inv, te) && (dist - te) > DRT_EPS;
 }
 
+// accepted?  (the entry t is not needed: root gates, left children of the literal recursion)
+__device__ __forceinline__ bool boxHit(const double* __restrict__ mn, const double* __restrict__ mx, const Ray& r, const D3& inv) {
+  double te; const int q = boxQuick(mn, mx, r, inv, te);
+  if (q >= 0) return q != 0;
+  int face; return boxTest(mn, mx, r, te, face);
+}
+// accepted AND (no hit yet OR entry t < tCur): the right-child rule of myBVH.traverseStruct (myGeomBase.java:413-417); the exact entry t is
+// formed only when the approximate one is within 1e-13 (relative) of tCur
+__device__ __forceinline__ bool boxHitBefore(const double* __restrict__ mn, const double* __restrict__ mx, const Ray& r, const D3& inv, double tCur) {
+  double te; const int q = boxQuick(mn, mx, r, inv, te);
+  if (q == 0) return false;
+  if (q > 0) { if (!(tCur < DRT_DMAX)) return true; const double m = 1e-13 * (fabs(te) + fabs(tCur)); if (te < tCur - m) return true; if (te > tCur + m) return false; }
+  if (!boxTestFx(mn, mx, r, inv, te)) return false;
+  return !(tCur < DRT_DMAX) || te < tCur;
+}
+
 // ---- primitives. `r` is the ray in the primitive's space, rawDir the direction recorded in the hit.
 // Returns true and fills h (t, loc, args, state) on a hit. time: ray time for moving spheres.
 __device__ __noinline__ bool primTest(const DScene& S, int primIdx, const Ray& r, double time, PHit& h) {
@@ -599,18 +615,18 @@ __device__ __forceinline__ double leafClosest(const DScene& S, int listIdx, Ray&
 // per-subtree minima needed for the pruning decisions live on an explicit frame stack.
 template <int LVL>
 __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc) {
-  double te; int face;
+  const D3 inv = rayInv(trans);
   if (kind == OK_LIST) {
     const FList& L = S.lists[idx];
     if (tc) ++tc->box;
-    if (!boxTest(L.bmin, L.bmax, trans, te, face)) return false;
+    if (!boxHit(L.bmin, L.bmax, trans, inv)) return false;
     XfCache xc; xc.xf = -1;
     double t = leafClosest<LVL>(S, idx, _ray, time, out, tc, xc);
     return t < DRT_DMAX;
   }
   const FBvh& B = S.bvhs[idx];
   if (tc) ++tc->box;
-  if (!boxTest(B.bmin, B.bmax, trans, te, face)) return false;
+  if (!boxHit(B.bmin, B.bmax, trans, inv)) return false;
   if (S.accelMode != 0 && B.fast != 0) {
     const double len2 = _ray.norm ? 1.0 : dot3(_ray.d, _ray.d);
     if (fastUsable(S, B, len2)) {
@@ -622,7 +638,6 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
       return one ? fastClosest<true>(S, B, trans, r, _ray.d, out, tc) : fastClosest<false>(S, B, trans, r, _ray.d, out, tc);
     }
   }
-  const D3 inv = rayInv(trans);
   XfCache xc; xc.xf = -1;
   Hit& best = out; hitReset(best);
   Hit leaf; hitReset(leaf);
@@ -639,15 +654,14 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
     } else {
       const FNode& N = S.nodes[node];
       if (tc) ++tc->box;
-      if (boxTestFx(N.lmin, N.lmax, trans, inv, te) && sp < DRT_STACK) { stack[sp].node = node; stack[sp].tL = 0; ++sp; node = N.left; tCur = DRT_DMAX; continue; }
+      if (boxHit(N.lmin, N.lmax, trans, inv) && sp < DRT_STACK) { stack[sp].node = node; stack[sp].tL = 0; ++sp; node = N.left; tCur = DRT_DMAX; continue; }
       tCur = DRT_DMAX; afterLeftOf = node;
     }
     while (true) {
       if (afterLeftOf >= 0) {          // left subtree of `afterLeftOf` finished with tCur
         const FNode& N = S.nodes[afterLeftOf];
         if (tc) ++tc->box;
-        bool hr = boxTestFx(N.rmin, N.rmax, trans, inv, te);
-        if (hr && (!(tCur < DRT_DMAX) || te < tCur) && sp < DRT_STACK) { stack[sp].node = -1; stack[sp].tL = tCur; ++sp; node = N.right; tCur = DRT_DMAX; ret = false; break; }
+        if (boxHitBefore(N.rmin, N.rmax, trans, inv, tCur) && sp < DRT_STACK) { stack[sp].node = -1; stack[sp].tL = tCur; ++sp; node = N.right; tCur = DRT_DMAX; ret = false; break; }
         afterLeftOf = -1; ret = true;  // result of this node = tL (an untraversed right box can never win: te >= tL)
       }
       if (ret) {
@@ -703,7 +717,7 @@ __device__ __forceinline__ bool listShadow(const DScene& S, int listIdx, Ray& _r
   const FList L = S.lists[listIdx];
   double te;
   if (tc) ++tc->box;
-  if (!(boxTestFx(L.bmin, L.bmax, trans, inv, te) && (dist - te) > DRT_EPS)) return false;
+  if (!boxAcceptShadow(L.bmin, L.bmax, trans, inv, dist)) return false;
   for (int i = 0; i < L.childCount; ++i) {
     const FObjRef c = S.children[L.childStart + i];
     Ray r = xfRayCached(S, _ray, c.xform, xc);
@@ -738,8 +752,8 @@ __device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const
     else {
       const FNode& N = S.nodes[node];
       if (tc) tc->box += 2;
-      bool hl = boxTestFx(N.lmin, N.lmax, trans, inv, te) && (dist - te) > DRT_EPS;
-      bool hr = boxTestFx(N.rmin, N.rmax, trans, inv, te) && (dist - te) > DRT_EPS;
+      bool hl = boxAcceptShadow(N.lmin, N.lmax, trans, inv, dist);
+      bool hr = boxAcceptShadow(N.rmin, N.rmax, trans, inv, dist);
       if (hl) { if (hr && sp < DRT_STACK) stack[sp++] = N.right; node = N.left; continue; }
       if (hr) { node = N.right; continue; }
     }
