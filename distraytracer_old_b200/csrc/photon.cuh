@@ -362,7 +362,24 @@ __global__ void __launch_bounds__(128) k_photon_gather(const __grid_constant__ D
   if (i < n && S.numPhotons > 0) { const SurfRec s = surf[i]; if (s.valid) { shIdx = s.shader; const FShader& sh = S.shaders[shIdx];
       needs = !(sh.flags & SF_SIMPLE) && (sh.KRefl == 0.0) && (sh.flags & SF_USE_PHOTON); loc = d3(s.loc[0], s.loc[1], s.loc[2]);
       // every lane prepares ITS query (cell range, candidate counts, search plan) in parallel; only the candidate scan is warp-serial
-      if (needs) { needs = phCellRange(S, loc, S.g.phMaxDist2, lo, hi); const uint32_t cnt = needs ? phCountCandidates(S, lo, hi) : 0u; needs = cnt > 0; few = cnt <= (uint32_t)S.g.kNhood; if (needs) phMakePlan(S, loc, cnt, lo, hi, pl); }
+      if (needs) { needs = phCellRange(S, loc, S.g.phMaxDist2, lo, hi); const uint32_t cnt = needs ? phCountCandidates(S, lo, hi) : 0u; needs = cnt > 0; few = cnt <= (uint32_t)S.g.kNhood;
+        if (needs && few) {
+          // Sparse neighbourhood (the candidate cells hold <= k photons): nothing to select, so the lane serves its own query -- 32 queries in
+          // parallel instead of one warp-wide scan each.  Sum order = photon order in the sorted array (deterministic, partition independent).
+          const double r2 = S.g.phMaxDist2; const double4* __restrict__ P = reinterpret_cast<const double4*>(S.phPos); const double4* __restrict__ W = reinterpret_cast<const double4*>(S.phPwr);
+          double s0 = 0, s1 = 0, s2 = 0, mx = 0;
+          for (int cz = lo[2]; cz <= hi[2]; ++cz) for (int cy = lo[1]; cy <= hi[1]; ++cy) {
+            const uint32_t row = ((uint32_t)cz * S.gridDim[1] + (uint32_t)cy) * S.gridDim[0];
+            const uint32_t a = S.cellStart[(size_t)(row + lo[0]) << 6], b = S.cellStart[(size_t)(row + hi[0] + 1) << 6];
+            for (uint32_t j = a; j < b; ++j) { const double4 q = P[j]; const double dx = loc.x - q.x, dy = loc.y - q.y, dz = loc.z - q.z, d2 = dx * dx + dy * dy + dz * dz;
+              if (d2 < r2) { const double4 w = W[j]; s0 += w.x; s1 += w.y; s2 += w.z; mx = fmax(mx, d2); } }
+          }
+          if (mx > 0) { const double area = DRT_PI_F * mx; const D3 irr = d3(s0 / area, s1 / area, s2 / area); double* l = nodes[i].local;
+            if (sh.flags & SF_IS_CAUSTIC_PHTN) { l[0] = l[0] + irr.x; l[1] = l[1] + irr.y; l[2] = l[2] + irr.z; }
+            else { l[0] = l[0] + sh.diff[0] * irr.x; l[1] = l[1] + sh.diff[1] * irr.y; l[2] = l[2] + sh.diff[2] * irr.z; } }
+          needs = false;
+        }
+        if (needs) phMakePlan(S, loc, cnt, lo, hi, pl); }
     } }
   unsigned mask = __ballot_sync(0xffffffffu, needs);
   while (mask) {
