@@ -193,6 +193,9 @@ __global__ void k_photon_reorder(const PhotonRec* __restrict__ rec, const uint32
 #ifndef DRT_PH_CULL
 #define DRT_PH_CULL 0      // sphere-chord culling of cell rows: measured slower on B200 (profiles/r1_tuning.md) -- the per-row FP64 sqrt/divide costs more than the skipped cells
 #endif
+#ifndef DRT_PH_LANE_MAX
+#define DRT_PH_LANE_MAX 1024u     // candidate count up to which a lane serves its own query
+#endif
 #define DRT_PH_BINS 256
 #define DRT_PH_LIST 128
 struct PhWarpShared { uint32_t hist[DRT_PH_BINS]; double listD2[DRT_PH_LIST]; uint32_t listIdx[DRT_PH_LIST]; uint32_t listN; uint32_t pad[3]; };
@@ -353,74 +356,139 @@ __device__ __forceinline__ void phMakePlan(const DScene& S, D3 p, uint32_t coars
     const double rad = s * cf * (1.0 - 1e-6); pl.r2 = rad * rad; return;       // 1e-6: a photon's own fine index is a rounded quotient
   }
 }
-// One warp serves the 32 surface records it owns, one query at a time. Runs between k_shade (local = ambient) and k_light
-// (local += direct), which is the reference's accumulation order (myObjShader.java:413-425).
-__global__ void __launch_bounds__(128) k_photon_gather(const __grid_constant__ DScene S, long long n, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, Counters* ctr) {
-  __shared__ PhWarpShared shw[4];
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; const unsigned lane = threadIdx.x & 31;
-  bool needs = false, few = false; D3 loc = d3(0, 0, 0); int shIdx = -1; int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; PhPlan pl; pl.fineHalf = -1; pl.r2 = S.g.phMaxDist2; for (int k = 0; k < 3; ++k) pl.c[k] = pl.h[k] = 0;
-  if (i < n && S.numPhotons > 0) { const SurfRec s = surf[i]; if (s.valid) { shIdx = s.shader; const FShader& sh = S.shaders[shIdx];
-      needs = !(sh.flags & SF_SIMPLE) && (sh.KRefl == 0.0) && (sh.flags & SF_USE_PHOTON); loc = d3(s.loc[0], s.loc[1], s.loc[2]);
-      // every lane prepares ITS query (cell range, candidate counts, search plan) in parallel; only the candidate scan is warp-serial
-      if (needs) { needs = phCellRange(S, loc, S.g.phMaxDist2, lo, hi); const uint32_t cnt = needs ? phCountCandidates(S, lo, hi) : 0u; needs = cnt > 0; few = cnt <= (uint32_t)S.g.kNhood;
-        if (needs && few) {
-          // Sparse neighbourhood (the candidate cells hold <= k photons): nothing to select, so the lane serves its own query -- 32 queries in
-          // parallel instead of one warp-wide scan each.  Sum order = photon order in the sorted array (deterministic, partition independent).
-          const double r2 = S.g.phMaxDist2; const double4* __restrict__ P = reinterpret_cast<const double4*>(S.phPos); const double4* __restrict__ W = reinterpret_cast<const double4*>(S.phPwr);
-          double s0 = 0, s1 = 0, s2 = 0, mx = 0;
-          for (int cz = lo[2]; cz <= hi[2]; ++cz) for (int cy = lo[1]; cy <= hi[1]; ++cy) {
-            const uint32_t row = ((uint32_t)cz * S.gridDim[1] + (uint32_t)cy) * S.gridDim[0];
-            const uint32_t a = S.cellStart[(size_t)(row + lo[0]) << 6], b = S.cellStart[(size_t)(row + hi[0] + 1) << 6];
-            for (uint32_t j = a; j < b; ++j) { const double4 q = P[j]; const double dx = loc.x - q.x, dy = loc.y - q.y, dz = loc.z - q.z, d2 = dx * dx + dy * dy + dz * dz;
-              if (d2 < r2) { const double4 w = W[j]; s0 += w.x; s1 += w.y; s2 += w.z; mx = fmax(mx, d2); } }
-          }
-          if (mx > 0) { const double area = DRT_PI_F * mx; const D3 irr = d3(s0 / area, s1 / area, s2 / area); double* l = nodes[i].local;
-            if (sh.flags & SF_IS_CAUSTIC_PHTN) { l[0] = l[0] + irr.x; l[1] = l[1] + irr.y; l[2] = l[2] + irr.z; }
-            else { l[0] = l[0] + sh.diff[0] * irr.x; l[1] = l[1] + sh.diff[1] * irr.y; l[2] = l[2] + sh.diff[2] * irr.z; } }
-          needs = false;
+// ---- one query per lane, three tiers by the number of photons in the candidate cells (all exact):
+//   <= k              the lane sums its candidates itself (nothing to select)
+//   <= DRT_PH_LANE_MAX the lane runs a two-pass histogram selection itself (neighbouring lanes read the same photons: mostly uniform loads)
+//   larger            the warp serves the query cooperatively (phWarpGather), over a fine cube first when the neighbourhood is dense
+// Results per lane: sum of the k nearest powers and d^2 of the farthest (0 = no photon in range). `path` (optional) reports the tier taken.
+struct PhLaneShared { uint16_t laneHist[128 * 128]; };      // lane-private 128-bin histograms laid out [bin][thread]
+struct PhWarpTierShared { PhWarpShared warp[4]; };
+
+__device__ __forceinline__ void phLaneRows(const DScene& S, const int lo[3], const int hi[3], int cz, int cy, uint32_t& a, uint32_t& b) {
+  const uint32_t row = ((uint32_t)cz * S.gridDim[1] + (uint32_t)cy) * S.gridDim[0];
+  a = S.cellStart[(size_t)(row + lo[0]) << 6]; b = S.cellStart[(size_t)(row + hi[0] + 1) << 6];
+}
+// tiers 1 and 2; returns true when the query is left for the warp-cooperative tier
+__device__ inline bool phLaneTiers(const DScene& S, bool needs, D3 loc, PhLaneShared& sm, double sum[3], double& dmax2, int* path) {
+  const double r2 = S.g.phMaxDist2; const int K = S.g.kNhood;
+  sum[0] = sum[1] = sum[2] = 0; dmax2 = 0; if (path) *path = 0;
+  bool few = false; int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  needs = needs && S.numPhotons > 0 && K > 0;
+  if (needs) {
+    needs = phCellRange(S, loc, r2, lo, hi); const uint32_t cnt = needs ? phCountCandidates(S, lo, hi) : 0u; needs = cnt > 0; few = cnt <= (uint32_t)K;
+    const double4* __restrict__ P = reinterpret_cast<const double4*>(S.phPos); const double4* __restrict__ W = reinterpret_cast<const double4*>(S.phPwr);
+    if (needs && few) {                                                    // tier 1. Sum order = photon order in the sorted array
+      double s0 = 0, s1 = 0, s2 = 0, mx = 0;
+      for (int cz = lo[2]; cz <= hi[2]; ++cz) for (int cy = lo[1]; cy <= hi[1]; ++cy) {
+        uint32_t a, b; phLaneRows(S, lo, hi, cz, cy, a, b);
+        for (uint32_t j = a; j < b; ++j) { const double4 q = P[j]; const double dx = loc.x - q.x, dy = loc.y - q.y, dz = loc.z - q.z, d2 = dx * dx + dy * dy + dz * dz;
+          if (d2 < r2) { const double4 w = W[j]; s0 += w.x; s1 += w.y; s2 += w.z; mx = fmax(mx, d2); } }
+      }
+      sum[0] = s0; sum[1] = s1; sum[2] = s2; dmax2 = mx; needs = false; if (path) *path = 1;
+    }
+    if (needs && cnt <= DRT_PH_LANE_MAX) {                                 // tier 2
+      // pass 1 bins d^2 into the lane's histogram (bin index monotone in d^2) and finds the bin of the k-th neighbour; pass 2 sums the bins
+      // below it and resolves the boundary bin exactly from a register list sorted by (d^2, index). A boundary bin with more than 8 photons
+      // hands the query to the warp-cooperative tier.
+      const double bscale = 127.99999 / r2; uint16_t* h = sm.laneHist + threadIdx.x;
+      for (int b = 0; b < 128; ++b) h[b * 128] = 0;
+      int m = 0;
+      for (int cz = lo[2]; cz <= hi[2]; ++cz) for (int cy = lo[1]; cy <= hi[1]; ++cy) {
+        uint32_t a, b; phLaneRows(S, lo, hi, cz, cy, a, b);
+        for (uint32_t j = a; j < b; ++j) { const double4 q = P[j]; const double dx = loc.x - q.x, dy = loc.y - q.y, dz = loc.z - q.z, d2 = dx * dx + dy * dy + dz * dz;
+          if (d2 < r2) { ++m; ++h[(int)(d2 * bscale) * 128]; } }
+      }
+      if (m == 0) { needs = false; if (path) *path = 2; }
+      else {
+        int bsel = 128, below = 0;
+        if (m > K) { int c = 0; for (int b = 0; b < 128; ++b) { const int hb = h[b * 128]; if (c + hb >= K) { bsel = b; below = c; break; } c += hb; } }
+        const int need = K - below;                                       // photons to take from the boundary bin (m > K only)
+        double s0 = 0, s1 = 0, s2 = 0, mx = 0, ld[8]; uint32_t lj[8]; int ln = 0; bool overflow = false;
+        for (int cz = lo[2]; cz <= hi[2]; ++cz) for (int cy = lo[1]; cy <= hi[1]; ++cy) {
+          uint32_t a, b; phLaneRows(S, lo, hi, cz, cy, a, b);
+          for (uint32_t j = a; j < b; ++j) { const double4 q = P[j]; const double dx = loc.x - q.x, dy = loc.y - q.y, dz = loc.z - q.z, d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 < r2) { const int bin = (int)(d2 * bscale);
+              if (bin < bsel) { const double4 w = W[j]; s0 += w.x; s1 += w.y; s2 += w.z; mx = fmax(mx, d2); }
+              else if (bin == bsel) {
+                if (ln == 8) overflow = true;
+                else { int pos = ln; while (pos > 0 && (ld[pos - 1] > d2)) { ld[pos] = ld[pos - 1]; lj[pos] = lj[pos - 1]; --pos; } ld[pos] = d2; lj[pos] = j; ++ln; } } } }
         }
-        if (needs) phMakePlan(S, loc, cnt, lo, hi, pl); }
-    } }
+        if (!overflow) {
+          for (int t = 0; t < need && t < ln; ++t) { const double4 w = W[lj[t]]; s0 += w.x; s1 += w.y; s2 += w.z; mx = fmax(mx, ld[t]); }
+          sum[0] = s0; sum[1] = s1; sum[2] = s2; dmax2 = mx; needs = false; if (path) *path = 2;
+        }
+      }
+    }
+  }
+  return needs;
+}
+// tier 3 / 4: the warp serves its pending queries one at a time
+__device__ inline void phWarpTier(const DScene& S, bool pending, D3 loc, PhWarpTierShared& sm, double sum[3], double& dmax2, int* path) {
+  const unsigned lane = threadIdx.x & 31; const double r2 = S.g.phMaxDist2; const int K = S.g.kNhood;
+  bool few = false; int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; PhPlan pl; pl.fineHalf = -1; pl.r2 = r2; for (int k = 0; k < 3; ++k) pl.c[k] = pl.h[k] = 0;
+  bool needs = pending && S.numPhotons > 0 && K > 0;
+  if (needs) { needs = phCellRange(S, loc, r2, lo, hi); const uint32_t cnt = needs ? phCountCandidates(S, lo, hi) : 0u; needs = cnt > 0; few = cnt <= (uint32_t)K; if (needs) phMakePlan(S, loc, cnt, lo, hi, pl); }
   unsigned mask = __ballot_sync(0xffffffffu, needs);
   while (mask) {
     const int src = __ffs(mask) - 1; mask &= mask - 1;
-    D3 p = d3(__shfl_sync(0xffffffffu, loc.x, src), __shfl_sync(0xffffffffu, loc.y, src), __shfl_sync(0xffffffffu, loc.z, src));
+    const D3 p = d3(__shfl_sync(0xffffffffu, loc.x, src), __shfl_sync(0xffffffffu, loc.y, src), __shfl_sync(0xffffffffu, loc.z, src));
     const int fineHalf = __shfl_sync(0xffffffffu, pl.fineHalf, src);
-    int qlo[3], qhi[3]; double sum[3], dmax2; bool done = false;
+    int qlo[3], qhi[3]; double qs[3], qd; bool done = false;
     if (fineHalf > 0) {
       const double pr2 = __shfl_sync(0xffffffffu, pl.r2, src);
 #pragma unroll
       for (int k = 0; k < 3; ++k) { qlo[k] = __shfl_sync(0xffffffffu, pl.c[k], src); qhi[k] = fineHalf; }
-      done = phWarpGather(S, p, pr2, true, false, fineHalf, qlo, qhi, shw[threadIdx.x >> 5], sum, dmax2, nullptr);
+      done = phWarpGather(S, p, pr2, true, false, fineHalf, qlo, qhi, sm.warp[threadIdx.x >> 5], qs, qd, nullptr);
     }
     if (!done) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) { qlo[k] = __shfl_sync(0xffffffffu, lo[k], src); qhi[k] = __shfl_sync(0xffffffffu, hi[k], src); }
-      phWarpGather(S, p, S.g.phMaxDist2, false, __shfl_sync(0xffffffffu, (int)few, src) != 0, -1, qlo, qhi, shw[threadIdx.x >> 5], sum, dmax2, nullptr);
+      phWarpGather(S, p, r2, false, __shfl_sync(0xffffffffu, (int)few, src) != 0, -1, qlo, qhi, sm.warp[threadIdx.x >> 5], qs, qd, nullptr);
     }
-    if ((int)lane == src && dmax2 > 0) {
-      const double area = DRT_PI_F * dmax2; const D3 irr = d3(sum[0] / area, sum[1] / area, sum[2] / area); const FShader& sh = S.shaders[shIdx];
-      double* l = nodes[i].local;
-      if (sh.flags & SF_IS_CAUSTIC_PHTN) { l[0] = l[0] + irr.x; l[1] = l[1] + irr.y; l[2] = l[2] + irr.z; }
-      else { l[0] = l[0] + sh.diff[0] * irr.x; l[1] = l[1] + sh.diff[1] * irr.y; l[2] = l[2] + sh.diff[2] * irr.z; }
-    }
+    if ((int)lane == src) { sum[0] = qs[0]; sum[1] = qs[1]; sum[2] = qs[2]; dmax2 = qd; if (path) *path = done ? 4 : 3; }
     __syncwarp();
   }
-  (void)ctr;
 }
 
-// parity probe: irradiance estimate at explicit points (one warp per point): out = {sum r,g,b, dmax2, count visited}
+// Run between k_shade (local = ambient) and k_light (local += direct), which is the reference's accumulation order (myObjShader.java:413-425).
+// Two kernels so that the warp-cooperative tier keeps its occupancy (64 registers, 10 KB shared) and the lane tiers their histogram space:
+// k_photon_gather_lane resolves tiers 1-2 and marks what is left in SurfRec::pad, k_photon_gather_warp serves the marked queries.
+__device__ __forceinline__ void phApply(const DScene& S, int shIdx, const double sum[3], double dmax2, double* l) {
+  if (!(dmax2 > 0)) return;
+  const double area = DRT_PI_F * dmax2; const D3 irr = d3(sum[0] / area, sum[1] / area, sum[2] / area); const FShader& sh = S.shaders[shIdx];
+  if (sh.flags & SF_IS_CAUSTIC_PHTN) { l[0] = l[0] + irr.x; l[1] = l[1] + irr.y; l[2] = l[2] + irr.z; }
+  else { l[0] = l[0] + sh.diff[0] * irr.x; l[1] = l[1] + sh.diff[1] * irr.y; l[2] = l[2] + sh.diff[2] * irr.z; }
+}
+__global__ void __launch_bounds__(128) k_photon_gather_lane(const __grid_constant__ DScene S, long long n, SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes) {
+  __shared__ PhLaneShared sm;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  const SurfRec s = surf[i]; if (!s.valid) return;
+  const FShader& sh = S.shaders[s.shader];
+  const bool needs = !(sh.flags & SF_SIMPLE) && (sh.KRefl == 0.0) && (sh.flags & SF_USE_PHOTON);
+  double sum[3], dmax2; const bool pending = phLaneTiers(S, needs, d3(s.loc[0], s.loc[1], s.loc[2]), sm, sum, dmax2, nullptr);
+  surf[i].pad = pending ? 1 : 0;
+  if (needs && !pending) phApply(S, s.shader, sum, dmax2, nodes[i].local);
+}
+__global__ void __launch_bounds__(128) k_photon_gather_warp(const __grid_constant__ DScene S, long long n, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes) {
+  __shared__ PhWarpTierShared sm;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool pending = false; D3 loc = d3(0, 0, 0); int shIdx = -1;
+  if (i < n) { pending = surf[i].valid && surf[i].pad == 1; if (pending) { shIdx = surf[i].shader; loc = d3(surf[i].loc[0], surf[i].loc[1], surf[i].loc[2]); } }
+  if (!__any_sync(0xffffffffu, pending)) return;
+  double sum[3], dmax2; phWarpTier(S, pending, loc, sm, sum, dmax2, nullptr);
+  if (pending) phApply(S, shIdx, sum, dmax2, nodes[i].local);
+}
+
+// parity probe: the same routines at explicit points, one lane per point: out = {sum r,g,b, dmax2, tier taken}
 __global__ void __launch_bounds__(128) k_photon_probe(const __grid_constant__ DScene S, long long n, const double* __restrict__ pts, double* __restrict__ out) {
-  __shared__ PhWarpShared shw[4];
-  const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; if (q >= n) return;
-  double sum[3] = {0, 0, 0}, dmax2 = 0; unsigned long long vis = 0; int lo[3], hi[3]; const D3 p = d3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]);
-  if (phCellRange(S, p, S.g.phMaxDist2, lo, hi)) {      // same two-step search as k_photon_gather
-    const uint32_t cnt = phCountCandidates(S, lo, hi); bool done = false;
-    if (cnt > 0) { PhPlan pl; phMakePlan(S, p, cnt, lo, hi, pl);
-      if (pl.fineHalf > 0) done = phWarpGather(S, p, pl.r2, true, false, pl.fineHalf, pl.c, pl.h, shw[threadIdx.x >> 5], sum, dmax2, &vis);
-      if (!done) phWarpGather(S, p, S.g.phMaxDist2, false, cnt <= (uint32_t)S.g.kNhood, -1, lo, hi, shw[threadIdx.x >> 5], sum, dmax2, &vis); }
-  }
-  if ((threadIdx.x & 31) == 0) { out[5 * q] = sum[0]; out[5 * q + 1] = sum[1]; out[5 * q + 2] = sum[2]; out[5 * q + 3] = dmax2; out[5 * q + 4] = (double)vis; }
+  __shared__ PhLaneShared sl; __shared__ PhWarpTierShared sw;
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; const bool ok = q < n;
+  const D3 p = ok ? d3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]) : d3(0, 0, 0);
+  double sum[3], dmax2; int path = 0;
+  const bool pending = phLaneTiers(S, ok, p, sl, sum, dmax2, &path);
+  double s2[3], d2; int path2 = 0; phWarpTier(S, pending, p, sw, s2, d2, &path2);
+  if (pending) { sum[0] = s2[0]; sum[1] = s2[1]; sum[2] = s2[2]; dmax2 = d2; path = path2; }
+  if (ok) { out[5 * q] = sum[0]; out[5 * q + 1] = sum[1]; out[5 * q + 2] = sum[2]; out[5 * q + 3] = dmax2; out[5 * q + 4] = (double)path; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

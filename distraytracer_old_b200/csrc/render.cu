@@ -459,7 +459,7 @@ void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank,
       else k_trace<false><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.rays[cur].p, hitBuf, I.ctr);
       CK(cudaEventRecord(I.ev[2], st));
       k_shade<<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.rays[cur].p, hitBuf, I.surf.p, I.nodes.p + off, I.rays[cur ^ 1].p, I.nodes.p + off + n, I.ctr, nextCap);
-      if (I.ds.numPhotons > 0) { k_photon_gather<<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off, I.ctr); ++rs.kernelLaunches; }
+      if (I.ds.numPhotons > 0) { k_photon_gather_lane<<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off); k_photon_gather_warp<<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off); rs.kernelLaunches += 2; }
       CK(cudaEventRecord(I.ev[3], st));
       if (counters_ || (traceMode_ & 256)) k_light<true><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off, I.ctr);
       else k_light<false><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off, I.ctr);
@@ -540,7 +540,7 @@ void Renderer::probePhotons(long long n, const double* ptsHost, double* out5Host
   if (g_.photonKind != 0 && !I.photons.built) I.photons.emitAndBuild(I.ds, I.ctr, I.ctrHost, st);
   double *a, *b; CK(cudaMalloc(&a, n * 24)); CK(cudaMalloc(&b, n * 40));
   CK(cudaMemcpyAsync(a, ptsHost, n * 24, cudaMemcpyHostToDevice, st)); CK(cudaMemsetAsync(b, 0, n * 40, st));
-  if (I.ds.numPhotons > 0) k_photon_probe<<<gridFor(n * 32, 128), 128, 0, st>>>(I.ds, n, a, b);
+  if (I.ds.numPhotons > 0) k_photon_probe<<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, a, b);
   CK(cudaMemcpyAsync(out5Host, b, n * 40, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
   cudaFree(a); cudaFree(b);
 }

@@ -257,7 +257,7 @@ class Scene:
         return st
 
     def photon_probe(self, pts):
-        """kNN radiance gather at world points: rows of {sum r, sum g, sum b, d2 of the farthest, candidates visited}."""
+        """kNN radiance gather at world points: rows of {sum r, sum g, sum b, d2 of the farthest, gather tier taken (0 none, 1-4)}."""
         pts = np.ascontiguousarray(pts, dtype=np.float64)
         out = np.zeros((pts.shape[0], 5), dtype=np.float64)
         self.ctx._ck(self.L.drt_photon_probe(self.ctx.h, pts.shape[0], pts.ctypes.data, out.ctypes.data))

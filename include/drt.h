@@ -88,7 +88,7 @@ int64_t drt_dump_bvh(drt_ctx* ctx, int32_t top_index, int32_t* out, int64_t cap,
 int drt_obj_ctm(drt_ctx* ctx, int32_t top_index, double* out16);
 double drt_sample_u01(uint64_t seed, uint32_t stream, uint32_t a, uint32_t b, uint32_t c, uint32_t d);
 int64_t drt_get_photons(drt_ctx* ctx, double* out6, int64_t cap);   /* x,y,z,r,g,b per stored photon */
-/* kNN radiance gather at explicit world points (myKD_Tree.find_near + getIrradianceFromPhtnTree): out5 = {sum r, sum g, sum b, d^2 of the farthest, candidates visited} */
+/* kNN radiance gather at explicit world points (myKD_Tree.find_near + getIrradianceFromPhtnTree): out5 = {sum r, sum g, sum b, d^2 of the farthest, gather tier taken: 0 no photon in range, 1 lane sum, 2 lane selection, 3 warp over coarse rows, 4 warp over a fine cube} */
 int drt_photon_probe(drt_ctx* ctx, int64_t n, const double* pts3, double* out5);
 
 #ifdef __cplusplus
