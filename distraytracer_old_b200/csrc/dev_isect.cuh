@@ -679,12 +679,18 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
 __device__ __forceinline__ bool closestHit(const DScene& S, Ray& ray, double time, Hit& best, TraceCounters* tc) {
   hitReset(best);
   Hit h; hitReset(h);
+  Ray tr; int trXf = -1;        // consecutive top-level objects often share one CTM (a polygon soup read under one transform): the transformed
+                                // ray is a pure function of (ray, CTM), and `ray` is already unit length here, so it is formed once per run
   for (int i = 0; i < S.g.numTop; ++i) {
     const FObjRef o = S.top[i];
-    Ray tr = xfRay(ray, S.xforms[o.xform].inv);
+    if (o.xform != trXf || o.kind != OK_PRIM) { tr = xfRay(ray, S.xforms[o.xform].inv); trXf = (o.kind == OK_PRIM) ? o.xform : -1; }
     if (o.kind == OK_PRIM) {
       PHit ph; if (tc) ++tc->prim;
-      if (primTest(S, o.idx, tr, time, ph) && ph.t < best.t) takeHit(S, best, ph, o.idx, tr, ray.d, o.xform);
+      const int triIdx = (S.accelMode != 0) ? S.prims[o.idx].pad0 : -1;      // packed record of a plain top-level triangle (fast modes)
+      if (triIdx >= 0) {
+        int32_t rank; ph.arg0 = 0; ph.arg1 = 0; ph.boxRaw = 0;
+        if (leanTri(S.tris + triIdx, tr.o.x, tr.o.y, tr.o.z, tr.d.x, tr.d.y, tr.d.z, best.t, ph.t, ph.state, rank) && ph.t < best.t) takeHit(S, best, ph, o.idx, tr, ray.d, o.xform);
+      } else if (primTest(S, o.idx, tr, time, ph) && ph.t < best.t) takeHit(S, best, ph, o.idx, tr, ray.d, o.xform);
     } else {
       bool got; int shader = -1, serial = -1;
       if (o.kind == OK_INSTANCE) {
@@ -762,11 +768,17 @@ __device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const
   }
 }
 __device__ __forceinline__ bool anyHit(const DScene& S, Ray& ray, double time, double dist, TraceCounters* tc) {
+  Ray tr; int trXf = -1;
   for (int i = 0; i < S.g.numTop; ++i) {
     const FObjRef o = S.top[i];
-    Ray tr = xfRay(ray, S.xforms[o.xform].inv);
+    if (o.xform != trXf || o.kind != OK_PRIM) { tr = xfRay(ray, S.xforms[o.xform].inv); trXf = (o.kind == OK_PRIM) ? o.xform : -1; }
     PHit h;
-    if (o.kind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, o.idx, tr, time, h) && (dist - h.t) > DRT_EPS) return true; }
+    if (o.kind == OK_PRIM) {
+      if (tc) ++tc->prim;
+      const int triIdx = (S.accelMode != 0) ? S.prims[o.idx].pad0 : -1;
+      if (triIdx >= 0) { int32_t rank; if (leanTri(S.tris + triIdx, tr.o.x, tr.o.y, tr.o.z, tr.d.x, tr.d.y, tr.d.z, DRT_DMAX, h.t, h.state, rank) && (dist - h.t) > DRT_EPS) return true; }
+      else if (primTest(S, o.idx, tr, time, h) && (dist - h.t) > DRT_EPS) return true;
+    }
     else if (o.kind == OK_INSTANCE) {
       const FInstance I = S.instances[o.idx];
       if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, I.baseIdx, tr, time, h) && (dist - h.t) > DRT_EPS) return true; }

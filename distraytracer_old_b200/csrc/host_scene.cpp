@@ -558,6 +558,16 @@ void HostScene::finalize() {
   for (FBvh& B : bvhs) buildFastBvh(B);
   top.clear();
   for (const HGeom& gm : topGeoms_) { FObjRef r; r.kind = gm.kind; r.idx = gm.idx; r.xform = gm.xform; r.hitXform = gm.xform; top.push_back(r); }
+  // plain triangles of the top-level list get a packed record too (FPrim::pad0 = FTri index, -1 otherwise): the fast modes test them with the
+  // same lean routine as BVH leaves instead of the generic primitive switch
+  for (FPrim& P : prims) P.pad0 = -1;
+  for (const FObjRef& r : top) if (r.kind == OK_PRIM && prims[r.idx].type == PT_TRI && prims[r.idx].pad0 < 0) {
+    FList one; std::memset(&one, 0, sizeof(one)); one.childStart = (int)children.size(); one.childCount = 1;
+    FObjRef c = r; children.push_back(c);                       // temporary child entry so that packLeaf() can be reused verbatim
+    const int32_t code = packLeaf(one, r.xform, r.hitXform);
+    children.pop_back();
+    if (code >= 0) prims[r.idx].pad0 = code >> 3;
+  }
   g.numTop = (int)top.size(); g.numLights = (int)lights.size();
 }
 
