@@ -52,8 +52,8 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu):
-        self.gpu, self.rows, self.stop, self.t = gpu, [], False, None
+    def __init__(self, gpu, enabled=True):
+        self.gpu, self.rows, self.stop, self.t, self.enabled = gpu, [], False, None, enabled
 
     def _run(self):
         while not self.stop:
@@ -63,13 +63,17 @@ class ClockSampler:
                     self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.2)
 
     def __enter__(self):
-        self.t = threading.Thread(target=self._run, daemon=True); self.t.start(); return self
+        if self.enabled:
+            self.t = threading.Thread(target=self._run, daemon=True); self.t.start()
+        return self
 
     def __exit__(self, *a):
-        self.stop = True; self.t.join(timeout=6)
+        self.stop = True
+        if self.t is not None:
+            self.t.join(timeout=6)
 
     def summary(self):
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
@@ -197,7 +201,7 @@ def main():
         flush.fill_(1); step()
     barrier()
     gpu_ms, trace_ms, rays, launches, trace_launch_count = [], 0.0, 0, 0, 0
-    with ClockSampler(local) as cs:
+    with ClockSampler(local, enabled=(rank == 0)) as cs:          # one sampler per job: concurrent nvidia-smi queries from every rank serialise on the driver
         for _ in range(args.steps):
             flush.fill_(1)                       # L2 flush between timed iterations
             barrier()
