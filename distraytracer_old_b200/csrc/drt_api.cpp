@@ -68,6 +68,11 @@ int drt_scene_finalize(drt_ctx* ctx, int32_t accel_mode) {
 }
 int drt_scene_reupload(drt_ctx* ctx) { NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized) throw std::runtime_error("scene not finalized"); ctx->renderer->upload(*ctx->scene); }, DRT_ERR_STATE) }
 int drt_accel_info(drt_ctx* ctx, double* out4) { NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized || !out4) throw std::runtime_error("scene not finalized"); ctx->renderer->accelInfo(out4); }, DRT_ERR_STATE) }
+int drt_scene_counts(drt_ctx* ctx, int64_t* o) {
+  GUARD(ctx, { if (!o) throw std::runtime_error("null output"); ctx->scene->finalize(); const HostScene& s = *ctx->scene; std::memset(o, 0, 8 * sizeof(int64_t));
+    o[0] = (int64_t)s.tris.size(); for (const FBvh& B : s.bvhs) if (B.fast) { ++o[1]; o[3] += B.triCount; } for (const FPrim& P : s.prims) if (P.pad0 >= 0) ++o[2];
+    o[4] = (int64_t)s.children.size(); o[5] = (int64_t)s.pdata.size(); }, DRT_ERR_SCENE)
+}
 int drt_scene_info(drt_ctx* ctx, int32_t* o) {
   GUARD(ctx, { ctx->scene->finalize(); const HostScene& s = *ctx->scene; std::memset(o, 0, 16 * sizeof(int32_t));
     o[0] = s.g.cols; o[1] = s.g.rows; o[2] = s.g.spp; o[3] = (int)s.top.size(); o[4] = (int)s.lights.size(); o[5] = (int)s.prims.size(); o[6] = (int)s.instances.size(); o[7] = s.g.photonKind;

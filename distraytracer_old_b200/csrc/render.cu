@@ -28,7 +28,9 @@ struct alignas(16) NodeRec { double local[3], cA[3], cB[3], w[3]; int32_t parent
 struct PixMap { long long chunkPix, totalPix; int world, rank; };
 __host__ __device__ __forceinline__ long long absPixel(const PixMap& m, long long p) { return ((p / m.chunkPix) * m.world + m.rank) * m.chunkPix + (p % m.chunkPix); }
 
-struct Counters { unsigned long long primary, shadow, reflect, refract, box, prim, nextCount, boxC, primC, pad; };
+// primaryS / shadowS: the two counters every warp bumps are spread over 64 slots (block index & 63) and summed on the host -- one address for
+// four million warps per frame showed up as 13 % of k_shade's stall samples
+struct Counters { unsigned long long primary, shadow, reflect, refract, box, prim, nextCount, boxC, primC, pad; unsigned long long primaryS[64], shadowS[64]; };
 
 __device__ __forceinline__ void warpAdd(unsigned long long* dst, unsigned long long v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene S,
   if (hasB) emit(at + (hasA ? 1 : 0), 2, dirB, wB, ktB0, ktB1);
   // 0/1 flags: one ballot + popc per counter instead of a 64-bit shuffle tree
   { const unsigned bp = __ballot_sync(0xffffffffu, cPrimary != 0), bl = __ballot_sync(0xffffffffu, cRefl != 0), br = __ballot_sync(0xffffffffu, cRefr != 0);
-    if (lane == 0) { if (bp) atomicAdd(&ctr->primary, (unsigned long long)__popc(bp)); if (bl) atomicAdd(&ctr->reflect, (unsigned long long)__popc(bl)); if (br) atomicAdd(&ctr->refract, (unsigned long long)__popc(br)); } }
+    if (lane == 0) { if (bp) atomicAdd(&ctr->primaryS[blockIdx.x & 63], (unsigned long long)__popc(bp)); if (bl) atomicAdd(&ctr->reflect, (unsigned long long)__popc(bl)); if (br) atomicAdd(&ctr->refract, (unsigned long long)__popc(br)); } }
 }
 
 // Light pass: literal calcShadowColor, one thread per shaded hit, lights in list order, shadow rays traced in-thread.
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(128, DRT_LIGHT_MINBLOCKS) k_light(const __grid
       nodes[i].local[0] += r; nodes[i].local[1] += g; nodes[i].local[2] += b;
     }
   }
-  warpAdd(&ctr->shadow, cShadow);
+  warpAdd(&ctr->shadowS[blockIdx.x & 63], cShadow);
   if (COUNT) { warpAdd(&ctr->box, tc.box); warpAdd(&ctr->prim, tc.prim); }
 }
 
@@ -479,6 +481,7 @@ void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank,
     k_finish<<<gridFor(nPix, 256), 256, 0, st>>>(I.ds, pm, b0, nPix, I.nodes.p, I.hits0.p, out); ++rs.kernelLaunches;
     CK(cudaMemcpyAsync(I.ctrHost, I.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    for (int k = 0; k < 64; ++k) { rs.primary += I.ctrHost->primaryS[k]; rs.shadow += I.ctrHost->shadowS[k]; }
     rs.primary += I.ctrHost->primary; rs.shadow += I.ctrHost->shadow; rs.reflect += I.ctrHost->reflect; rs.refract += I.ctrHost->refract; rs.boxTests += I.ctrHost->box; rs.primTests += I.ctrHost->prim; rs.boxTestsClosest += I.ctrHost->boxC; rs.primTestsClosest += I.ctrHost->primC;
   }
   CK(cudaEventRecord(I.ev[5], st)); CK(cudaStreamSynchronize(st));

@@ -62,6 +62,7 @@ int drt_scene_override(drt_ctx* ctx, int32_t spp, int64_t photons); /* <=0 / <0 
 int drt_scene_finalize(drt_ctx* ctx, int32_t accel_mode);        /* flatten, build acceleration structures, upload to HBM */
 int drt_scene_reupload(drt_ctx* ctx);                            /* host->device copy of the flattened scene again (used by end-to-end timing) */
 int drt_accel_info(drt_ctx* ctx, double* out4);                  /* after finalize: GPU LBVH build ms, triangles and nodes it covers, scene bytes resident in HBM */
+int drt_scene_counts(drt_ctx* ctx, int64_t* out8);               /* flattener products of the fast paths: packed triangles, fast BVHs, packed top-level triangles, triangles in fast BVHs, children, pdata doubles, 0, 0 */
 int drt_scene_info(drt_ctx* ctx, int32_t* out16);                /* cols, rows, spp, top objects, lights, prims, instances, photon kind, shaders, nodes, xforms, lists, ... */
 
 /* ---- rendering: replaces myScene.initRender + draw; argb layout == PImage.pixels ---- */

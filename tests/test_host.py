@@ -148,3 +148,18 @@ def test_chunk_partition_covers_every_pixel_once():
         assert (seen == 1).all()
     lo = [D.photon_range(1000003, 8, r) for r in range(8)]
     assert lo[0][0] == 0 and lo[-1][1] == 1000003 and all(lo[i][1] == lo[i + 1][0] for i in range(7))
+
+
+def test_fast_path_packing(drt):
+    """Host flattener products the fast traversal modes rely on: every triangle of a pure-triangle BVH gets one packed record (the object the
+    reference drops, SURVEY Q2, excepted), plain top-level triangles get one too, BVHs with mixed children / differing CTMs do not qualify."""
+    ctx = drt.Context(device=-1)
+    c = drt.Scene.from_cli(ctx, "p3_t08.cli", finalize=False).counts()          # bun500 (966 triangles) in a BVH + 2 floor triangles
+    assert c["fast_bvhs"] == 1 and c["tris_in_fast_bvhs"] == 965 and c["top_tris_packed"] == 2 and c["tris_packed"] == 967
+    c = drt.Scene.from_cli(ctx, "t01.cli", finalize=False).counts()             # spheres only
+    assert c["tris_packed"] == 0 and c["fast_bvhs"] == 0
+    c = drt.Scene.from_cli(ctx, "box_caustics.cli", finalize=False).counts()    # 12 box triangles in the top-level list
+    assert c["top_tris_packed"] == 12 and c["fast_bvhs"] == 0
+    c = drt.Scene.from_cli(ctx, "p3_t02_sierp.cli", finalize=False).counts()    # instance BVH over a sphere: nothing to pack
+    assert c["fast_bvhs"] == 0
+    ctx.close()
