@@ -88,7 +88,10 @@ __device__ inline bool phSpecular(const DScene& S, const FShader& sh, const PhHi
 }
 
 // one thread = photon index (i0 + g / numLights) of light (g % numLights); stores go to fixed slots g*maxStore.. and are compacted afterwards
-__global__ void __launch_bounds__(128) k_photon_emit(const __grid_constant__ DScene S, long long i0, long long nThreads, int maxStore, PhotonRec* __restrict__ slots, uint32_t* __restrict__ slotCount, Counters* ctr) {
+#ifndef DRT_EMIT_MINBLOCKS
+#define DRT_EMIT_MINBLOCKS 4      // 128 registers: 16 M photons in 14.7 ms vs 22.9 ms at 255 registers (profiles/r1_tuning.md)
+#endif
+__global__ void __launch_bounds__(128, DRT_EMIT_MINBLOCKS) k_photon_emit(const __grid_constant__ DScene S, long long i0, long long nThreads, int maxStore, PhotonRec* __restrict__ slots, uint32_t* __restrict__ slotCount, Counters* ctr) {
   long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; unsigned long long segs = 0;
   if (g < nThreads) {
     const int nl = S.g.numLights; PhSampler sp; sp.seed = S.g.seed; sp.photon = (uint32_t)(i0 + g / nl); sp.light = (uint32_t)(g % nl);
