@@ -86,7 +86,7 @@ __device__ __forceinline__ double rayTime(const DScene& S, uint32_t stream, uint
 }
 
 #ifndef DRT_TRACE_MINBLOCKS
-#define DRT_TRACE_MINBLOCKS 6
+#define DRT_TRACE_MINBLOCKS 5
 #endif
 #ifndef DRT_LIGHT_MINBLOCKS
 #define DRT_LIGHT_MINBLOCKS 6
@@ -129,7 +129,10 @@ __device__ inline D3 skyColor(const DScene& S, D3 o, D3 d) {
 }
 
 // Surface pass. One thread per ray of the level; children go to the next level's queue.
-__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DScene S, long long n, const RayRec* __restrict__ rays, const Hit* __restrict__ hits,
+#ifndef DRT_SHADE_MINBLOCKS
+#define DRT_SHADE_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, DRT_SHADE_MINBLOCKS) k_shade(const __grid_constant__ DScene S, long long n, const RayRec* __restrict__ rays, const Hit* __restrict__ hits,
                                                SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, RayRec* __restrict__ nextRays, NodeRec* __restrict__ nextNodes,
                                                Counters* ctr, long long nextCap) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
