@@ -32,6 +32,19 @@ __host__ __device__ __forceinline__ long long absPixel(const PixMap& m, long lon
 // four million warps per frame showed up as 13 % of k_shade's stall samples
 struct Counters { unsigned long long primary, shadow, reflect, refract, box, prim, nextCount, boxC, primC, pad; unsigned long long primaryS[64], shadowS[64]; };
 
+// 16-byte-granular streaming (evict-first) copies of the 16-byte-aligned wavefront records
+template <class T> __device__ __forceinline__ void streamLoad(T* dst, const T* src) {
+  static_assert(sizeof(T) % 16 == 0, "record size");
+  int4* d = reinterpret_cast<int4*>(dst); const int4* q = reinterpret_cast<const int4*>(src);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(T) / 16); ++k) d[k] = __ldcs(q + k);
+}
+template <class T> __device__ __forceinline__ void streamStore(T* dst, const T* src) {
+  static_assert(sizeof(T) % 16 == 0, "record size");
+  int4* d = reinterpret_cast<int4*>(dst); const int4* q = reinterpret_cast<const int4*>(src);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(T) / 16); ++k) __stcs(d + k, q[k]);
+}
 __device__ __forceinline__ void warpAdd(unsigned long long* dst, unsigned long long v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
@@ -96,12 +109,14 @@ __global__ void __launch_bounds__(128, DRT_TRACE_MINBLOCKS) k_trace(const __grid
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   TraceCounters tc; tc.box = 0; tc.prim = 0;
   if (i < n) {
-    const RayRec r = rays[i]; Hit h; hitReset(h);
+    // the ray / hit records are pure streams (read once, written once): evict-first loads and stores keep them from pushing the scene and the
+    // local-memory traversal state out of L2
+    RayRec r; streamLoad(&r, rays + i); Hit h; hitReset(h);
     if (r.valid) {
       Ray ray = makeRay(d3(r.o[0], r.o[1], r.o[2]), d3(r.d[0], r.d[1], r.d[2]));
       closestHit(S, ray, rayTime(S, r.stream, r.ka, r.kb, r.kc, r.stream == STREAM_PIXEL ? DIM_TIME : 0xFFFFu), h, COUNT ? &tc : nullptr);
     }
-    hits[i] = h;
+    streamStore(hits + i, &h);
   }
   if (COUNT) { warpAdd(&ctr->box, tc.box); warpAdd(&ctr->prim, tc.prim); warpAdd(&ctr->boxC, tc.box); warpAdd(&ctr->primC, tc.prim); }
 }
