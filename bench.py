@@ -270,6 +270,11 @@ def main():
                 "traffic": None, "peak_source": which + " (burst copy)", "per_ray": {"box_tests": round(box_per_ray, 2), "prim_tests": round(prim_per_ray, 2), "bytes": round(bytes_per_ray, 1)},
                 "ms_trace_per_step": round(ms_trace_step, 3), "launches_per_step": n_trace_launches,
                 "note": "traversal is issue/latency bound with an L2-resident scene (SURVEY 8(d)); bytes are algorithmic bytes touched, not DRAM traffic; see profiles/ for ncu dram bytes and issue-slot utilisation"}
+        # the same kernel against the bytes that MUST cross HBM (record in + record out; the scene is cache resident) and against the issue-slot
+        # roofline (ncu, profiles/r1c_ncu_k_trace.md): these two say what actually bounds it
+        compulsory = closest_rays_per_step * 192.0 / (ms_trace_step / 1e3) / 1e9
+        roof["compulsory_hbm"] = {"achieved": round(compulsory, 1), "unit": "GB/s", "frac": round(compulsory / peaks["hbm_gbs"], 4), "bytes_per_ray": 192}
+        roof["issue_slots_ncu"] = {"util": 0.446, "fp64_pipe": 0.284, "source": "profiles/r1c_ncu_k_trace.md (sm__inst_issued.avg.pct_of_peak_sustained_active)"}
         tr_path = os.path.join(ROOT, "profiles", "trace_traffic.json")
         if os.path.exists(tr_path):
             try:
