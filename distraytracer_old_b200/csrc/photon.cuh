@@ -332,7 +332,8 @@ __device__ inline uint32_t phCountCandidates(const DScene& S, const int lo[3], c
   return c;
 }
 // Dense neighbourhoods: the k-th neighbour is far closer than r, so most of the r-sphere's candidates are wasted work.  Per query (lane-parallel):
-//   count the photons in the fine cube of half-width 1, then 2, around p's fine cell; the first one that holds >= 4k photons gives the plan
+//   count the photons in the fine cube of half-width 1, 2, 3 around p's fine cell; the first one expected to hold >= 1.25 k photons inside its
+//   inscribed search sphere gives the plan
 //   "search radius s * fineCell over that cube" -- exact if >= k photons turn out to lie inside that radius (every photon closer than s fine
 //   cells to p is in the cube), otherwise the caller falls back to the full radius over the coarse rows.
 struct PhPlan { int fineHalf; int c[3]; int h[3]; double r2; };      // fineHalf < 0: coarse rows c..h with threshold r2
@@ -354,7 +355,9 @@ __device__ __forceinline__ void phMakePlan(const DScene& S, D3 p, uint32_t coars
   const double cf = S.cellSize * 0.25, pp[3] = {p.x, p.y, p.z}; int f[3]; bool inside = true;
   for (int k = 0; k < 3; ++k) { const double a = floor((pp[k] - S.gridMin[k]) / cf); const int fd = 4 * (int)S.gridDim[k]; if (!(a >= 0) || !(a <= fd - 1)) inside = false; f[k] = (int)a; }
   if (!inside) return;
-  for (int s = 1; s <= 2; ++s) if (phCountFineCube(S, f, s) >= (uint32_t)(4 * K)) {
+  // expected share of a cube's photons that lie inside the sphere of radius s fine cells (surface distribution): pi s^2 / (2s+1)^2
+  const double frac[4] = {0.0, 0.349, 0.503, 0.577};
+  for (int s = 1; s <= 3; ++s) if ((double)phCountFineCube(S, f, s) * frac[s] >= 1.25 * K) {
     pl.fineHalf = s; for (int k = 0; k < 3; ++k) { pl.c[k] = f[k]; pl.h[k] = s; }
     const double rad = s * cf * (1.0 - 1e-6); pl.r2 = rad * rad; return;       // 1e-6: a photon's own fine index is a rounded quotient
   }
