@@ -36,6 +36,11 @@ __device__ __forceinline__ void hitReset(Hit& h) { h.t = DRT_DMAX; h.prim = -1; 
 
 struct TraceCounters { unsigned long long box, prim; };
 
+// device-side error word, checked by the host after every render / trace / photon call (bit 0: a traversal stack overflowed -- the result
+// would silently miss geometry, so the call fails instead)
+__device__ unsigned int g_devError;
+__device__ __forceinline__ void flagError(unsigned int bit) { if (!(g_devError & bit)) atomicOr(&g_devError, bit); }
+
 __device__ __forceinline__ Ray makeRay(D3 o, D3 dirNormalized) { Ray r; r.o = o; r.d = dirNormalized; r.a = dirNormalized; r.norm = true; return r; }
 // getTransformedRay: normalise the source direction in place (only if it is not already unit length: canonical mode,
 // see DESIGN.md "re-normalisation"), transform origin as a point and direction as a vector, do NOT normalise the result.
@@ -309,7 +314,7 @@ struct FStack {
     if (sp < DRT_SSTACK) g_fstk[sp * DRT_TB + threadIdx.x] = e; else
 #endif
     if (sp < DRT_FSTACK) ovf[sp - DRT_SSTACK] = e;
-    if (sp < DRT_FSTACK) ++sp;
+    if (sp < DRT_FSTACK) ++sp; else flagError(1u);
   }
   __device__ __forceinline__ uint2 pop() {
     --sp;
@@ -654,6 +659,7 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
     } else {
       const FNode& N = S.nodes[node];
       if (tc) ++tc->box;
+      if (sp >= DRT_STACK) flagError(1u);
       if (boxHit(N.lmin, N.lmax, trans, inv) && sp < DRT_STACK) { stack[sp].node = node; stack[sp].tL = 0; ++sp; node = N.left; tCur = DRT_DMAX; continue; }
       tCur = DRT_DMAX; afterLeftOf = node;
     }
@@ -760,7 +766,7 @@ __device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const
       if (tc) tc->box += 2;
       bool hl = boxAcceptShadow(N.lmin, N.lmax, trans, inv, dist);
       bool hr = boxAcceptShadow(N.rmin, N.rmax, trans, inv, dist);
-      if (hl) { if (hr && sp < DRT_STACK) stack[sp++] = N.right; node = N.left; continue; }
+      if (hl) { if (hr) { if (sp < DRT_STACK) stack[sp++] = N.right; else flagError(1u); } node = N.left; continue; }
       if (hr) { node = N.right; continue; }
     }
     if (sp == 0) return false;

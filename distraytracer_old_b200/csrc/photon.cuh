@@ -190,12 +190,6 @@ __global__ void k_photon_reorder(const PhotonRec* __restrict__ rec, const uint32
 // ---------------------------------------------------------------------------------------------------------------
 // gather
 // ---------------------------------------------------------------------------------------------------------------
-#ifndef DRT_PH_PRECHECK
-#define DRT_PH_PRECHECK 1
-#endif
-#ifndef DRT_PH_CULL
-#define DRT_PH_CULL 0      // sphere-chord culling of cell rows: measured slower on B200 (profiles/r1_tuning.md) -- the per-row FP64 sqrt/divide costs more than the skipped cells
-#endif
 #ifndef DRT_PH_LANE_MAX
 #define DRT_PH_LANE_MAX 1024u     // candidate count up to which a lane serves its own query
 #endif

@@ -20,6 +20,12 @@ namespace drt {
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x); } while (0)
 
+static void devErrorReset(cudaStream_t st) { const unsigned int z = 0; CK(cudaMemcpyToSymbolAsync(g_devError, &z, sizeof(z), 0, cudaMemcpyHostToDevice, st)); }
+static void devErrorCheck(cudaStream_t st) {
+  unsigned int e = 0; CK(cudaMemcpyFromSymbolAsync(&e, g_devError, sizeof(e), 0, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+  if (e & 1u) throw std::runtime_error("traversal stack overflow on the device (acceleration structure deeper than the kernels support): the result would be incomplete");
+}
+
 struct alignas(16) RayRec { double o[3], d[3]; double kt0, kt1; uint32_t ka, kb, kc, stream; int32_t gen, valid; int32_t pad[2]; };
 struct alignas(16) SurfRec { double loc[3], n[3], rawDir[3], tex[3]; int32_t shader, valid; uint32_t ka, kb, kc, stream; int32_t gen, pad; };
 struct alignas(16) NodeRec { double local[3], cA[3], cB[3], w[3]; int32_t parent, slot; int32_t pad[2]; };
@@ -456,6 +462,7 @@ void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank,
   if (pm.world > 1) { long long nChunks = (g_.rows + chunkRows - 1) / chunkRows, mine = (nChunks - rank + world - 1) / world; pix0 = 0; pix1 = mine * pm.chunkPix; }
   if (!I.ds.prims) throw std::runtime_error("render called before a scene was uploaded");
   const unsigned long long buildLaunches0 = g_kernelLaunches;
+  devErrorReset(st);
   if (g_.photonKind != 0 && !I.photons.built) { if (!I.photons.emitted) I.photons.emitRange(I.ds, 0, g_.numPhotonsCast, I.ctr, I.ctrHost, st); I.photons.buildGrid(I.ds, st); }
   const int spp = g_.spp < 1 ? 1 : g_.spp;
   long long pixPerBatch = batchRays_ / spp; if (pixPerBatch < 1) pixPerBatch = 1;
@@ -505,6 +512,7 @@ void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank,
   CK(cudaEventRecord(I.ev[5], st)); CK(cudaStreamSynchronize(st));
   float tot; CK(cudaEventElapsedTime(&tot, I.ev[0], I.ev[5]));
   CK(cudaGetLastError());
+  devErrorCheck(st);
   rs.kernelLaunches += g_kernelLaunches - buildLaunches0;      // photon emission / grid build done inside this call
   rs.msTrace = msT; rs.msShade = msS; rs.msLight = msL; rs.msTotal = tot; rs.msOther = tot - msT - msS - msL;
   if (stats) *stats = rs;
@@ -531,7 +539,9 @@ void Renderer::renderToHost(int32_t* argbHost, int32_t* hitPrimHost, int32_t* hi
 double hostPhiloxU01(uint64_t seed, uint32_t stream, uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return philoxU01(seed, stream, a, b, c, d); }
 void Renderer::emitPhotons(RenderStats* stats) {
   CK(cudaSetDevice(device_)); Impl& I = *impl_; const unsigned long long l0 = g_kernelLaunches;
+  devErrorReset((cudaStream_t)stream_);
   if (g_.photonKind != 0 && !I.photons.built) I.photons.emitAndBuild(I.ds, I.ctr, I.ctrHost, (cudaStream_t)stream_);
+  devErrorCheck((cudaStream_t)stream_);
   if (stats) { stats->kernelLaunches = g_kernelLaunches - l0; stats->photonsStored = I.photons.count; stats->photonSeg = I.photons.segments; stats->msTrace = I.photons.msEmit; stats->msOther = I.photons.msBuild; stats->msTotal = I.photons.msEmit + I.photons.msBuild; }
 }
 // multi-GPU split: emit photon indices [i0, i1) of every light (no grid build); export / import the canonical-order records on the device
@@ -540,7 +550,9 @@ void Renderer::emitPhotonsRange(long long i0, long long i1, RenderStats* stats) 
   if (g_.photonKind == 0) { I.photons.reset(); return; }
   if (i0 < 0 || i1 > g_.numPhotonsCast || i0 > i1) throw std::runtime_error("photon index range outside [0, photons cast]");
   const unsigned long long l0 = g_kernelLaunches;
+  devErrorReset((cudaStream_t)stream_);
   I.photons.emitRange(I.ds, i0, i1, I.ctr, I.ctrHost, (cudaStream_t)stream_);
+  devErrorCheck((cudaStream_t)stream_);
   if (stats) { stats->kernelLaunches = g_kernelLaunches - l0; stats->photonsStored = I.photons.count; stats->photonSeg = I.photons.segments; stats->msTrace = I.photons.msEmit; stats->msTotal = I.photons.msEmit; }
 }
 long long Renderer::exportPhotonsDevice(double* dst6Dev, long long cap) {
@@ -570,12 +582,13 @@ long long Renderer::getPhotons(double* out6Host, long long cap) { CK(cudaSetDevi
 
 void Renderer::traceRays(long long n, const double* orgHost, const double* dirHost, int32_t* idsHost, double* tHost) {
   CK(cudaSetDevice(device_)); cudaStream_t st = (cudaStream_t)stream_;
+  devErrorReset(st);
   double *o, *d, *t; int32_t* ids; CK(cudaMalloc(&o, n * 24)); CK(cudaMalloc(&d, n * 24)); CK(cudaMalloc(&t, n * 8)); CK(cudaMalloc(&ids, n * 8));
   CK(cudaMemcpyAsync(o, orgHost, n * 24, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(d, dirHost, n * 24, cudaMemcpyHostToDevice, st));
   if (counters_) k_trace_explicit<true><<<gridFor(n, 128), 128, 0, st>>>(impl_->ds, n, o, d, ids, t);
   else k_trace_explicit<false><<<gridFor(n, 128), 128, 0, st>>>(impl_->ds, n, o, d, ids, t);
   CK(cudaMemcpyAsync(idsHost, ids, n * 8, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(tHost, t, n * 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st)); CK(cudaGetLastError()); devErrorCheck(st);
   cudaFree(o); cudaFree(d); cudaFree(t); cudaFree(ids);
 }
 void Renderer::evalTexture(int shaderIdx, long long n, const double* hitLocHost, const double* fwdLocHost, double* outHost) {
