@@ -33,6 +33,8 @@ WORKLOADS = {
                     desc="configs[3]: textured planets, bunny BVHs, reflection/refraction, spot + point lights"),
     "box_caustics": dict(scene="box_caustics.cli", cols=3840, rows=2160, spp=16, photons=4000000, metric="Mrays/s (all ray types incl. photon segments), box caustics 4K 16spp",
                          desc="configs[4]: Cornell wrapper around data/box.cli, caustic photon map k=80 r=0.05; photon pass inside every step"),
+    "t11": dict(scene="t11.cli", cols=3840, rows=2160, spp=16, photons=1000000, metric="Mrays/s (all ray types incl. photon segments), t11 Cornell box 4K 16spp",
+                desc="the reference scene behind its shipped box-caustics renders (t11c.png, boxCaustics*.png): Cornell box, mirror + glass spheres, point + disk light, diffuse photon map k=200 r=0.1"),
     "box_gi": dict(scene="box_gi.cli", cols=3840, rows=2160, spp=16, photons=1000000, metric="Mrays/s (all ray types incl. photon segments), box diffuse-GI 4K 16spp",
                    desc="configs[4] diffuse variant: diffuse photon map k=200 r=0.1; photon pass inside every step"),
 }

@@ -82,6 +82,20 @@ def test_planets_bunnies_config4(drt, orc, gpu_ctx_factory):
     check_scene(drt, orc, gpu_ctx_factory, "plnts3ColsBunnies", cols=120, rows=120, spp=4, stochastic=True)
 
 
+def test_reference_render_t11_sierp(drt, orc, gpu_ctx_factory):
+    """The CUDA path against the reference's OWN shipped render (t11_sierp.png <- data/project3/p3_t11_sierp.cli, deterministic; the mesh is the
+    bun69k stand-in, so the comparison is PSNR after a 4x4 box filter, see tests/test_oracle.py for the oracle's figure: 34.6 dB)."""
+    from PIL import Image
+    ref = np.asarray(Image.open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_t11_sierp.png")).convert("RGB")).astype(float)
+    for accel in (drt.ACCEL_REFERENCE, drt.ACCEL_REFERENCE_FAST, drt.ACCEL_LBVH):
+        ctx = gpu_ctx_factory(300, 300)
+        argb, _ = drt.Scene.from_cli(ctx, "p3_t11_sierp_d6.cli", accel=accel).draw()
+        img = orc.argb_to_rgb8(argb).astype(float)
+        box = lambda a: a.reshape(75, 4, 75, 4, 3).mean(axis=(1, 3))
+        assert 10 * np.log10(255 ** 2 / ((box(img) - box(ref)) ** 2).mean()) > 31.0, accel
+        ctx.close()
+
+
 def test_golden_fixtures(drt, orc, gpu_ctx_factory, golden):
     for name, n in (("t01", 64), ("t03", 64), ("p3_t08", 64), ("p3_t02_sierp", 64), ("p3_t12", 64), ("p3_t06", 48), ("c5Fish", 48), ("planets3Ortho", 40), ("p2_t06", 32), ("t06", 48)):
         ctx = gpu_ctx_factory(n, n)

@@ -68,6 +68,24 @@ def test_reference_image_t11c_loose_pin(orc):
     assert psnr > 24.0, psnr
 
 
+def test_reference_image_t11_sierp_pin(orc):
+    """t11_sierp.png is the reference's own render of data/project3/p3_t11_sierp.cli (Sierpinski depth 6 of bun69k instances, skydome, two
+    lights, per-level pastel shaders) -- a DETERMINISTIC scene, so the only differences to the oracle are the stand-in mesh (bun69k.cli is
+    missing from the checkout; tools/make_bun69k.py) and the unknown code revision.  It exercises the instance generator (Appendix B), the
+    instance-level BVH with its non-conservative boxes (Q5), mixed t units (Q7), the CTM double application (Q6: the black bunnies), shading
+    and the skydome lookup.  Measured: 23.7 dB per pixel, 34.6 dB after a 4x4 box filter."""
+    from PIL import Image
+    ref = np.asarray(Image.open(os.path.join(ROOT, "tests", "golden", "ref_t11_sierp.png")).convert("RGB")).astype(float)
+    s = orc.OracleScene("p3_t11_sierp_d6.cli")
+    img = orc.argb_to_rgb8(s.render(threads=os.cpu_count(), want=("argb",))["argb"]).astype(float)
+
+    def box(a):
+        return a.reshape(75, 4, 75, 4, 3).mean(axis=(1, 3))
+    psnr_px = 10 * np.log10(255 ** 2 / ((img - ref) ** 2).mean())
+    psnr_box = 10 * np.log10(255 ** 2 / ((box(img) - box(ref)) ** 2).mean())
+    assert psnr_px > 21.0 and psnr_box > 31.0, (psnr_px, psnr_box)
+
+
 def test_bvh_median_split_ledger(orc, golden):
     s = orc.OracleScene("p3_t08.cli")
     d, box = s.dump_bvh(2)
