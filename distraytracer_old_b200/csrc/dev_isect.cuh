@@ -727,7 +727,6 @@ __device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const
 template <int LVL>
 __device__ __forceinline__ bool listShadow(const DScene& S, int listIdx, Ray& _ray, const Ray& trans, const D3& inv, double time, double dist, TraceCounters* tc, XfCache& xc) {
   const FList L = S.lists[listIdx];
-  double te;
   if (tc) ++tc->box;
   if (!boxAcceptShadow(L.bmin, L.bmax, trans, inv, dist)) return false;
   for (int i = 0; i < L.childCount; ++i) {
@@ -758,7 +757,6 @@ __device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const
     return one ? fastShadow<true>(S, B, trans, r, dist, tc) : fastShadow<false>(S, B, trans, r, dist, tc);
   }
   int32_t stack[DRT_STACK]; int sp = 0; int32_t node = B.root;
-  double te;
   while (true) {
     if (node < 0) { if (listShadow<LVL>(S, ~node, _ray, trans, inv, time, dist, tc, xc)) return true; }
     else {
