@@ -62,6 +62,7 @@ int drt_scene_load_cli(drt_ctx* ctx, const char* file, const char* data_dir) {
 int drt_scene_override(drt_ctx* ctx, int32_t spp, int64_t photons) { GUARD(ctx, { ctx->spp = spp; ctx->photons = photons; }, DRT_ERR_SCENE) }
 int drt_scene_finalize(drt_ctx* ctx, int32_t accel_mode) {
   GUARD(ctx, {
+    if ((accel_mode & 3) == 3 || (accel_mode & ~(3 | 256 | 512)) != 0) throw std::runtime_error("unknown acceleration mode (use DRT_ACCEL_REFERENCE, DRT_ACCEL_REFERENCE_FAST or DRT_ACCEL_LBVH)");
     ctx->scene->overrideSpp(ctx->spp); ctx->scene->overridePhotons(ctx->photons);
     ctx->scene->finalize();
     if (ctx->renderer) { ctx->renderer->setTraceMode(accel_mode); ctx->renderer->upload(*ctx->scene); ctx->finalized = true; } }, DRT_ERR_SCENE)

@@ -163,3 +163,12 @@ def test_fast_path_packing(drt):
     c = drt.Scene.from_cli(ctx, "p3_t02_sierp.cli", finalize=False).counts()    # instance BVH over a sphere: nothing to pack
     assert c["fast_bvhs"] == 0
     ctx.close()
+
+
+def test_unknown_accel_mode_is_rejected(drt):
+    ctx = drt.Context(device=-1)
+    s = drt.Scene.from_cli(ctx, "t01.cli", finalize=False)
+    with pytest.raises(drt.DrtError):
+        s.finalize(7)
+    s.finalize(drt.ACCEL_LBVH)          # host-only context: flattening succeeds, nothing is uploaded
+    ctx.close()
