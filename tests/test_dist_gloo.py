@@ -25,6 +25,12 @@ WORKER = textwrap.dedent("""
         print("GATHER_OK")
     else:
         assert frame is None
+    # same through a buffer padded to whole chunks per rank (what bench.py allocates: the pack is then a strided view, no copy)
+    padded = torch.zeros(D.padded_pixels(rows, cols, world), dtype=torch.int32)
+    padded[:rows * cols] = local
+    frame2 = D.gather_frame(padded, rows, cols, world, rank, dist)
+    if rank == 0:
+        assert torch.equal(frame2, want), "assembled frame (padded buffer) differs"
     # photon exchange: ranks own contiguous photon-index ranges with a different number of stored records each; the gathered set must be
     # the rank-order concatenation (== the single-GPU canonical order)
     n_cast = 1003
