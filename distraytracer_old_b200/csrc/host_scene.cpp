@@ -15,7 +15,7 @@ struct Missing {};
 struct HostScene::Tokens {
   std::vector<std::string> t;
   explicit Tokens(const std::string& line) {
-    size_t p = 0, n = line.size();
+    size_t p = 0, n = line.size(); t.reserve(8);
     while (p < n) { while (p < n && line[p] == ' ') ++p; size_t q = p; while (q < n && line[q] != ' ') ++q; if (q > p) t.push_back(line.substr(p, q - p)); p = q; }
   }
   size_t size() const { return t.size(); }
@@ -86,6 +86,10 @@ void HostScene::rotate(double deg, double ax, double ay, double az) {
   mulTop(mmul(mtranspose(toX), mmul(aboutX, toX)));
 }
 int HostScene::xformOf(const M4& m) {
+  if (lastXform_ >= 0 && std::memcmp(lastXformM_.a, m.a, sizeof(m.a)) == 0) return lastXform_;     // every polygon of a mesh asks for the same CTM
+  const int r = xformOfSlow(m); lastXform_ = r; lastXformM_ = m; return r;
+}
+int HostScene::xformOfSlow(const M4& m) {
   std::string key((const char*)m.a, sizeof(m.a));
   auto it = xformCache_.find(key); if (it != xformCache_.end()) return it->second;
   FXform x; M4 inv = minverse(m), adj = mtranspose(inv);
@@ -173,6 +177,7 @@ int HostScene::currentShader() {
   // dedupe on the full snapshot
   std::string key((const char*)&s, sizeof(s)); key.append((const char*)&t, sizeof(t)); key.append((const char*)cols.data(), cols.size() * sizeof(double));
   auto& cache = shaderCache_;
+  if (lastShader_ >= 0 && key == lastShaderKey_) { shaderOfSerial.push_back(lastShader_); return lastShader_; }     // consecutive polygons of one mesh
   int idx; auto it = cache.find(key);
   if (it != cache.end()) idx = it->second;
   else {
@@ -180,7 +185,7 @@ int HostScene::currentShader() {
     s.tex = (int)textures.size(); textures.push_back(t);
     s.serial = (int)shaders.size(); idx = (int)shaders.size(); shaders.push_back(s); cache[key] = idx;
   }
-  shaderOfSerial.push_back(idx);
+  shaderOfSerial.push_back(idx); lastShader_ = idx; lastShaderKey_ = key;
   return idx;
 }
 
@@ -422,6 +427,9 @@ void HostScene::command(const std::string& line) {
   if (k.size() == 0 || k.t[0][0] == '#') return;
   const std::string& c = k.t[0];
   try {
+    // meshes are >99 % `vertex` / `begin` / `end` lines: dispatch them before the long chain of command names (same handlers as below)
+    if (c == "vertex") { if (poly_.active && poly_.cnt < poly_.n) { poly_.v[poly_.cnt][0] = k.num(1); poly_.v[poly_.cnt][1] = k.num(2); poly_.v[poly_.cnt][2] = k.num(3); } poly_.cnt++; return; }
+    if (c == "end") { endPoly(); vertType_ = "triangle"; return; }
     if (c == "fov" || c == "fishEye" || c == "fisheye" || c == "ortho" || c == "orthographic") {
       if (!isMain_) { warnings.push_back("scene type in child file ignored"); return; }
       g.spp = (curSpp_ != 0) ? curSpp_ : 1;

@@ -71,6 +71,8 @@ class HostScene {
   void push(); void pop(); void mulTop(const M4& m);
   void translate(double x, double y, double z); void scale(double x, double y, double z); void rotate(double deg, double ax, double ay, double az);
   int xformOf(const M4& m);
+  int xformOfSlow(const M4& m);
+  int lastXform_ = -1; M4 lastXformM_;
   std::map<std::string, int> xformCache_;
   // material / texture state (myScene.java:117-145)
   struct Mat { V3 diff, amb, spec, perm, kreflClr; double phong = 0, krefl = 0, ktrans = 0, rfrIdx = 0; } mat_;
@@ -82,7 +84,7 @@ class HostScene {
   void resetTxtrDefaults();
   void setTexture(const Tokens& k); void setNoiseColor(const Tokens& k);
   int currentShader();                 // getCurShader(): snapshot, deduped against the previous snapshot
-  std::map<std::string, int> shaderCache_;
+  std::map<std::string, int> shaderCache_; int lastShader_ = -1; std::string lastShaderKey_;
   // objects
   std::vector<HGeom> topGeoms_, tmpList_; std::vector<bool> allIsLight_; bool toTmp_ = false;
   std::map<std::string, HGeom> named_;
