@@ -8,7 +8,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-MESH_SCENES = ["p3_t08", "p3_t09", "p3_t10", "p3_t11", "p3_t11_sierp", "p4_t06", "plnts3ColsBunnies", "p3_t12", "p3_t05"]
+MESH_SCENES = ["p3_t08", "p3_t09", "p3_t10", "p3_t11", "p3_t11_sierp", "p4_t06", "plnts3ColsBunnies", "p3_t12", "p3_t05",
+               "t03", "t06", "t07", "c2clear", "p2_t05", "box_caustics"]      # the last six: plain top-level triangles / quads (lean top-level path), no BVH
 
 
 def render(drt, make, name, accel, cols, rows, spp=0, **kw):
