@@ -14,6 +14,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2", "-shared", "--expt-relaxed-constexpr", "--extended-lambda"]
 
 
+LINK_FLAGS = ["-lz", "-ldl"]
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
@@ -29,7 +32,7 @@ def build(force=False, verbose=False, out=None, defines=()):
     if out is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out or LIB, "-lz"]
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out or LIB] + LINK_FLAGS
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -306,15 +306,16 @@ __device__ __forceinline__ bool boxTestStd(const double* mn, const double* mx, c
 #if DRT_SSTACK > 0
 __shared__ uint2 g_fstk[DRT_SSTACK * DRT_TB];
 #endif
-struct FStack {
-  uint2 ovf[DRT_FSTACK - DRT_SSTACK]; int sp = 0;
+template <int CAP>
+struct FStackT {
+  uint2 ovf[CAP - DRT_SSTACK]; int sp = 0; bool overflow = false;
   __device__ __forceinline__ void push(int32_t ref, float te) {
     const uint2 e = make_uint2((uint32_t)ref, __float_as_uint(te));
 #if DRT_SSTACK > 0
     if (sp < DRT_SSTACK) g_fstk[sp * DRT_TB + threadIdx.x] = e; else
 #endif
-    if (sp < DRT_FSTACK) ovf[sp - DRT_SSTACK] = e;
-    if (sp < DRT_FSTACK) ++sp; else flagError(1u);
+    if (sp < CAP) ovf[sp - DRT_SSTACK] = e;
+    if (sp < CAP) ++sp; else overflow = true;
   }
   __device__ __forceinline__ uint2 pop() {
     --sp;
@@ -324,6 +325,18 @@ struct FStack {
     return ovf[sp - DRT_SSTACK];
   }
 };
+typedef FStackT<DRT_FSTACK> FStack;
+// Compile-time feature set of a tracing kernel (see render.cu): the lean kernels carry only the code their scene shape needs -- a small
+// local frame and register budget -- and hand the rare ray they cannot serve (axis-parallel direction, mixed units through an instance,
+// traversal deeper than the short stack) to the generic kernel through a deferral list.  Every ray is traced start to finish by ONE variant,
+// and all variants implement the same rules, so results do not depend on which one served a ray.
+enum : int { TF_LITERAL1 = 1,     // literal (reference-order) BVH recursion at the top level, lists holding instanced accels
+             TF_LEVEL2 = 2,       // literal recursion / non-lean descent inside instanced accels
+             TF_NONLEAN = 4,      // near-first descent with the generic slab test (irregular directions) at the top level
+             TF_ALL = 7 };
+#ifndef DRT_LSTACK
+#define DRT_LSTACK 32            // short traversal stack of the lean kernels (a <=5-per-leaf median tree over 2^24 triangles is 23 deep)
+#endif
 __device__ __forceinline__ int32_t childRef(int32_t link, int32_t triCode) { return link >= 0 ? link : ~triCode; }
 
 // Closest hit inside one fast BVH (root box already accepted by the caller). `trans` is the ray the boxes are tested with,
@@ -367,6 +380,7 @@ __device__ DRT_LEAN_INLINE bool fastClosest(const DScene& S, const FBvh& B, cons
     // pop
     while (true) {
       if (stk.sp == 0) {
+        if (stk.overflow) flagError(1u);
         if (bestTri < 0) return false;
         out.t = bestT; out.prim = S.tris[bestTri].prim; out.arg0 = 0; out.arg1 = 0; out.state = bestSt; out.hitXform = B.triHitXform; out.shaderOverride = -1; out.inst = -1;
         out.loc = pointOnRay(r, bestT); out.rawDir = rawDir; return true;
@@ -404,7 +418,7 @@ __device__ DRT_LEAN_INLINE bool fastShadow(const DScene& S, const FBvh& B, const
         if (triTestPacked(w, r, t, st) && (dist - t) > DRT_EPS) return true;
       }
     }
-    if (stk.sp == 0) return false;
+    if (stk.sp == 0) { if (stk.overflow) flagError(1u); return false; }
     ref = (int32_t)stk.pop().x;
   }
 }
@@ -472,14 +486,15 @@ __device__ __forceinline__ bool leanTri(const FTri* __restrict__ T, double ox, d
   rank = __ldg(reinterpret_cast<const int32_t*>(T) + 29);
   tOut = t; stOut = st; return true;
 }
-template <bool ONE_RAY>
-__device__ DRT_LEAN_INLINE bool leanClosest(const DScene& S, const FBvh& B, const D3 bo, const D3 ba, const D3 to, const D3 td, const D3 rawDir, Hit& out, TraceCounters* tc) {
+// returns 1 hit / 0 miss / -1 the CAP-entry stack overflowed (the caller defers the ray to the generic kernel or flags a device error)
+template <bool ONE_RAY, int CAP>
+__device__ DRT_LEAN_INLINE int leanClosest(const DScene& S, const FBvh& B, const D3 bo, const D3 ba, const D3 to, const D3 td, const D3 rawDir, Hit& out, TraceCounters* tc) {
   LeanRay R; R.ox = bo.x; R.oy = bo.y; R.oz = bo.z;
   const double ax = ba.x, ay = ba.y, az = ba.z;
   R.ix = 1.0 / ax; R.iy = 1.0 / ay; R.iz = 1.0 / az; R.px = ax > 0; R.py = ay > 0; R.pz = az > 0;
   const double tox = ONE_RAY ? R.ox : to.x, toy = ONE_RAY ? R.oy : to.y, toz = ONE_RAY ? R.oz : to.z;
   const double tdx = ONE_RAY ? ax : td.x, tdy = ONE_RAY ? ay : td.y, tdz = ONE_RAY ? az : td.z;
-  FStack stk; const bool stdBox = S.accelMode == 2;
+  FStackT<CAP> stk; const bool stdBox = S.accelMode == 2;
   double bestT = DRT_DMAX; int bestTri = -1, bestRank = 0x7fffffff, bestSt = 0;
   int32_t ref = B.fastRoot;
   while (true) {
@@ -512,23 +527,24 @@ __device__ DRT_LEAN_INLINE bool leanClosest(const DScene& S, const FBvh& B, cons
     }
     while (true) {
       if (stk.sp == 0) {
-        if (bestTri < 0) return false;
+        if (stk.overflow) return -1;
+        if (bestTri < 0) return 0;
         out.t = bestT; out.prim = S.tris[bestTri].prim; out.arg0 = 0; out.arg1 = 0; out.state = bestSt; out.hitXform = B.triHitXform; out.shaderOverride = -1; out.inst = -1;
-        out.loc = d3((tdx * bestT) + tox, (tdy * bestT) + toy, (tdz * bestT) + toz); out.rawDir = rawDir; return true;
+        out.loc = d3((tdx * bestT) + tox, (tdy * bestT) + toy, (tdz * bestT) + toz); out.rawDir = rawDir; return 1;
       }
       const uint2 e = stk.pop();
       if ((double)__uint_as_float(e.y) < bestT) { ref = (int32_t)e.x; break; }
     }
   }
 }
-template <bool ONE_RAY>
-__device__ DRT_LEAN_INLINE bool leanShadow(const DScene& S, const FBvh& B, const D3 bo, const D3 ba, const D3 to, const D3 td, double dist, TraceCounters* tc) {
+template <bool ONE_RAY, int CAP>
+__device__ DRT_LEAN_INLINE int leanShadow(const DScene& S, const FBvh& B, const D3 bo, const D3 ba, const D3 to, const D3 td, double dist, TraceCounters* tc) {
   LeanRay R; R.ox = bo.x; R.oy = bo.y; R.oz = bo.z;
   const double ax = ba.x, ay = ba.y, az = ba.z;
   R.ix = 1.0 / ax; R.iy = 1.0 / ay; R.iz = 1.0 / az; R.px = ax > 0; R.py = ay > 0; R.pz = az > 0;
   const double tox = ONE_RAY ? R.ox : to.x, toy = ONE_RAY ? R.oy : to.y, toz = ONE_RAY ? R.oz : to.z;
   const double tdx = ONE_RAY ? ax : td.x, tdy = ONE_RAY ? ay : td.y, tdz = ONE_RAY ? az : td.z;
-  FStack stk; const bool stdBox = S.accelMode == 2;
+  FStackT<CAP> stk; const bool stdBox = S.accelMode == 2;
   int32_t ref = B.fastRoot;
   auto accept = [&](int q, double te, const double* box6) {       // (dist - entry) > eps, with the exact entry t only when it is too close to call
     if (q == 0) return false;
@@ -554,10 +570,10 @@ __device__ DRT_LEAN_INLINE bool leanShadow(const DScene& S, const FBvh& B, const
       const int code = ~ref, cnt = code & 7, first = code >> 3;
       for (int i = 0; i < cnt; ++i) {
         double t; int st; int32_t rank; if (tc) ++tc->prim;
-        if (leanTri(S.tris + first + i, tox, toy, toz, tdx, tdy, tdz, DRT_DMAX, t, st, rank) && (dist - t) > DRT_EPS) return true;
+        if (leanTri(S.tris + first + i, tox, toy, toz, tdx, tdy, tdz, DRT_DMAX, t, st, rank) && (dist - t) > DRT_EPS) return 1;
       }
     }
-    if (stk.sp == 0) return false;
+    if (stk.sp == 0) return stk.overflow ? -1 : 0;
     ref = (int32_t)stk.pop().x;
   }
 }
@@ -570,13 +586,11 @@ __device__ __forceinline__ bool fastUsable(const DScene& S, const FBvh& B, doubl
 #define DRT_STACK 48
 struct Frame { int32_t node; double tL; };     // node >= 0: "after left" of that node; node == -1: "after right", tL saved
 
-struct XfCache;
-
 // ---------------------------------------------------------------------------------------------------------------
-// closest hit
+// closest hit.  Every function returns 1 (hit), 0 (miss) or -1 (this kernel variant cannot serve the ray: defer it)
 // ---------------------------------------------------------------------------------------------------------------
-template <int LVL>
-__device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc);
+template <int F, int LVL>
+__device__ int accelClosest(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc);
 
 // myGeomList.traverseStruct: every child gets a fresh transform of `_ray`; first strictly smaller t wins;
 // the winner's CTM becomes list.CTM x child.CTM (child.hitXform).
@@ -586,8 +600,8 @@ __device__ __forceinline__ const Ray& xfRayCached(const DScene& S, Ray& _ray, in
   if (xc.xf != xf) { xc.r = xfRay(_ray, S.xforms[xf].inv); xc.xf = xf; }
   return xc.r;
 }
-template <int LVL>
-__device__ __forceinline__ double leafClosest(const DScene& S, int listIdx, Ray& _ray, double time, Hit& res, TraceCounters* tc, XfCache& xc) {
+template <int F, int LVL>
+__device__ __forceinline__ double leafClosest(const DScene& S, int listIdx, Ray& _ray, double time, Hit& res, TraceCounters* tc, XfCache& xc, bool& defer) {
   const FList L = S.lists[listIdx];
   double clsT = DRT_DMAX;
   for (int i = 0; i < L.childCount; ++i) {
@@ -601,11 +615,16 @@ __device__ __forceinline__ double leafClosest(const DScene& S, int listIdx, Ray&
       if (I.baseKind == OK_PRIM) {
         PHit ph; if (tc) ++tc->prim;
         if (primTest(S, I.baseIdx, r, time, ph) && ph.t < clsT) { clsT = ph.t; takeHit(S, res, ph, I.baseIdx, r, r.d, c.hitXform); if (I.shader >= 0) res.shaderOverride = I.shader; res.inst = I.serial; }
-      } else if (LVL == 1) {
-        Hit h; hitReset(h);
-        if (accelClosest<2>(S, I.baseKind, I.baseIdx, r, r, time, h, tc) && h.t < clsT) {
-          clsT = h.t; res.t = h.t; res.prim = h.prim; res.arg0 = h.arg0; res.arg1 = h.arg1; res.state = h.state; res.loc = h.loc; res.rawDir = h.rawDir;
-          res.hitXform = c.hitXform; res.shaderOverride = (I.shader >= 0) ? I.shader : h.shaderOverride; res.inst = (h.inst < 0) ? I.serial : h.inst;
+      } else if constexpr (LVL == 1) {
+        if constexpr (!(F & TF_LITERAL1)) { defer = true; return clsT; }
+        else {
+          Hit h; hitReset(h);
+          const int got = accelClosest<F, 2>(S, I.baseKind, I.baseIdx, r, r, time, h, tc);
+          if (got < 0) { defer = true; return clsT; }
+          if (got && h.t < clsT) {
+            clsT = h.t; res.t = h.t; res.prim = h.prim; res.arg0 = h.arg0; res.arg1 = h.arg1; res.state = h.state; res.loc = h.loc; res.rawDir = h.rawDir;
+            res.hitXform = c.hitXform; res.shaderOverride = (I.shader >= 0) ? I.shader : h.shaderOverride; res.inst = (h.inst < 0) ? I.serial : h.inst;
+          }
         }
       }
     }
@@ -618,32 +637,47 @@ __device__ __forceinline__ double leafClosest(const DScene& S, int listIdx, Ray&
 // (left found nothing or right-entry t < left result t); result = left if left.t <= right.t.  Because every level
 // combines with "min, left wins ties", the overall winner is the DFS-first minimum over all visited leaves; the
 // per-subtree minima needed for the pruning decisions live on an explicit frame stack.
-template <int LVL>
-__device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc) {
+template <int F, int LVL>
+__device__ int accelClosest(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc) {
+  constexpr bool LITERAL = (LVL == 1) ? ((F & TF_LITERAL1) != 0) : ((F & TF_LEVEL2) != 0);      // literal recursion compiled in at this level?
+  constexpr bool NONLEAN = (LVL == 1) ? ((F & TF_NONLEAN) != 0) : ((F & TF_LEVEL2) != 0);
   const D3 inv = rayInv(trans);
   if (kind == OK_LIST) {
     const FList& L = S.lists[idx];
     if (tc) ++tc->box;
-    if (!boxHit(L.bmin, L.bmax, trans, inv)) return false;
-    XfCache xc; xc.xf = -1;
-    double t = leafClosest<LVL>(S, idx, _ray, time, out, tc, xc);
-    return t < DRT_DMAX;
+    if (!boxHit(L.bmin, L.bmax, trans, inv)) return 0;
+    XfCache xc; xc.xf = -1; bool defer = false;
+    double t = leafClosest<F, LVL>(S, idx, _ray, time, out, tc, xc, defer);
+    if (defer) return -1;
+    return t < DRT_DMAX ? 1 : 0;
   }
   const FBvh& B = S.bvhs[idx];
   if (tc) ++tc->box;
-  if (!boxHit(B.bmin, B.bmax, trans, inv)) return false;
+  if (!boxHit(B.bmin, B.bmax, trans, inv)) return 0;
   if (S.accelMode != 0 && B.fast != 0) {
     const double len2 = _ray.norm ? 1.0 : dot3(_ray.d, _ray.d);
     if (fastUsable(S, B, len2)) {
       const Ray r = xfRay(_ray, S.xforms[B.triXform].inv);          // what every leaf child of this mesh would be tested with
       const bool one = sameRay(trans, r);
 #if DRT_LEAN
-      if (regularDir(trans.a)) return one ? leanClosest<true>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc) : leanClosest<false>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc);
+      if (regularDir(trans.a)) {
+        // one instantiation per lean kernel (one traversal stack in its frame): flat scenes test boxes and triangles with the same ray, scenes
+        // with instanced meshes need the two-ray form (which gives the same bits when both rays coincide); a flat-scene kernel defers the rest
+        if constexpr (F == TF_ALL) {
+          const int got = one ? leanClosest<true, DRT_FSTACK>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc) : leanClosest<false, DRT_FSTACK>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc);
+          if (got < 0) { flagError(1u); return 0; }
+          return got;
+        } else if constexpr ((F & TF_LITERAL1) != 0) return leanClosest<false, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc);
+        else { if (!one) return -1; return leanClosest<true, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc); }
+      }
 #endif
-      return one ? fastClosest<true>(S, B, trans, r, _ray.d, out, tc) : fastClosest<false>(S, B, trans, r, _ray.d, out, tc);
+      if constexpr (!NONLEAN) return -1;
+      else return (one ? fastClosest<true>(S, B, trans, r, _ray.d, out, tc) : fastClosest<false>(S, B, trans, r, _ray.d, out, tc)) ? 1 : 0;
     }
   }
-  XfCache xc; xc.xf = -1;
+  if constexpr (!LITERAL) return -1;
+  else {
+  XfCache xc; xc.xf = -1; bool defer = false;
   Hit& best = out; hitReset(best);
   Hit leaf; hitReset(leaf);
   Frame stack[DRT_STACK]; int sp = 0;
@@ -652,7 +686,8 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
     bool ret = false;
     int32_t afterLeftOf = -1;
     if (node < 0) {                    // leaf
-      tCur = leafClosest<LVL>(S, ~node, _ray, time, leaf, tc, xc);
+      tCur = leafClosest<F, LVL>(S, ~node, _ray, time, leaf, tc, xc, defer);
+      if (defer) return -1;
       if (tCur < best.t) { best.t = leaf.t; best.prim = leaf.prim; best.arg0 = leaf.arg0; best.arg1 = leaf.arg1; best.state = leaf.state; best.hitXform = leaf.hitXform;
         best.shaderOverride = leaf.shaderOverride; best.inst = leaf.inst; best.loc = leaf.loc; best.rawDir = leaf.rawDir; }
       ret = true;
@@ -671,7 +706,7 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
         afterLeftOf = -1; ret = true;  // result of this node = tL (an untraversed right box can never win: te >= tL)
       }
       if (ret) {
-        if (sp == 0) return best.t < DRT_DMAX;
+        if (sp == 0) return best.t < DRT_DMAX ? 1 : 0;
         --sp;
         if (stack[sp].node >= 0) { afterLeftOf = stack[sp].node; continue; }
         double tL = stack[sp].tL; tCur = (tL <= tCur) ? tL : tCur;       // min, left wins ties
@@ -679,10 +714,12 @@ __device__ bool accelClosest(const DScene& S, int kind, int idx, Ray& _ray, cons
       }
     }
   }
+  }
 }
 
 // myScene.findClosestRayHit: linear scan of the top-level list, first-inserted wins among equal t
-__device__ __forceinline__ bool closestHit(const DScene& S, Ray& ray, double time, Hit& best, TraceCounters* tc) {
+template <int F>
+__device__ __forceinline__ int closestHitT(const DScene& S, Ray& ray, double time, Hit& best, TraceCounters* tc) {
   hitReset(best);
   Hit h; hitReset(h);
   Ray tr; int trXf = -1;        // consecutive top-level objects often share one CTM (a polygon soup read under one transform): the transformed
@@ -698,7 +735,7 @@ __device__ __forceinline__ bool closestHit(const DScene& S, Ray& ray, double tim
         if (leanTri(S.tris + triIdx, tr.o.x, tr.o.y, tr.o.z, tr.d.x, tr.d.y, tr.d.z, best.t, ph.t, ph.state, rank) && ph.t < best.t) takeHit(S, best, ph, o.idx, tr, ray.d, o.xform);
       } else if (primTest(S, o.idx, tr, time, ph) && ph.t < best.t) takeHit(S, best, ph, o.idx, tr, ray.d, o.xform);
     } else {
-      bool got; int shader = -1, serial = -1;
+      int got; int shader = -1, serial = -1;
       if (o.kind == OK_INSTANCE) {
         const FInstance I = S.instances[o.idx]; shader = I.shader; serial = I.serial;
         if (I.baseKind == OK_PRIM) {
@@ -706,59 +743,76 @@ __device__ __forceinline__ bool closestHit(const DScene& S, Ray& ray, double tim
           if (primTest(S, I.baseIdx, tr, time, ph) && ph.t < best.t) { takeHit(S, best, ph, I.baseIdx, tr, tr.d, o.xform); if (shader >= 0) best.shaderOverride = shader; best.inst = serial; }
           continue;
         }
-        got = accelClosest<1>(S, I.baseKind, I.baseIdx, tr, tr, time, h, tc);
-      } else got = accelClosest<1>(S, o.kind, o.idx, ray, tr, time, h, tc);
+        got = accelClosest<F, 1>(S, I.baseKind, I.baseIdx, tr, tr, time, h, tc);
+      } else got = accelClosest<F, 1>(S, o.kind, o.idx, ray, tr, time, h, tc);
+      if (got < 0) return -1;
       if (got && h.t < best.t) {
         best.t = h.t; best.prim = h.prim; best.arg0 = h.arg0; best.arg1 = h.arg1; best.state = h.state; best.hitXform = h.hitXform; best.loc = h.loc; best.rawDir = h.rawDir;
         best.shaderOverride = (shader >= 0) ? shader : h.shaderOverride; best.inst = (serial >= 0 && h.inst < 0) ? serial : h.inst;
       }
     }
   }
-  return best.t < DRT_DMAX;
+  return best.t < DRT_DMAX ? 1 : 0;
 }
+__device__ __forceinline__ bool closestHit(const DScene& S, Ray& ray, double time, Hit& best, TraceCounters* tc) { return closestHitT<TF_ALL>(S, ray, time, best, tc) > 0; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // any hit (shadow rays): hit AND (distToLight - t) > eps.  The BVH form never tests its root box; every list
-// (top-level or BVH leaf) gates on its own box with the same rule.
+// (top-level or BVH leaf) gates on its own box with the same rule.  1 / 0 / -1 as above.
 // ---------------------------------------------------------------------------------------------------------------
-template <int LVL>
-__device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc);
+template <int F, int LVL>
+__device__ int accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc);
 
-template <int LVL>
-__device__ __forceinline__ bool listShadow(const DScene& S, int listIdx, Ray& _ray, const Ray& trans, const D3& inv, double time, double dist, TraceCounters* tc, XfCache& xc) {
+template <int F, int LVL>
+__device__ __forceinline__ int listShadow(const DScene& S, int listIdx, Ray& _ray, const Ray& trans, const D3& inv, double time, double dist, TraceCounters* tc, XfCache& xc) {
   const FList L = S.lists[listIdx];
   if (tc) ++tc->box;
-  if (!boxAcceptShadow(L.bmin, L.bmax, trans, inv, dist)) return false;
+  if (!boxAcceptShadow(L.bmin, L.bmax, trans, inv, dist)) return 0;
   for (int i = 0; i < L.childCount; ++i) {
     const FObjRef c = S.children[L.childStart + i];
     Ray r = xfRayCached(S, _ray, c.xform, xc);
     PHit h;
-    if (c.kind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, c.idx, r, time, h) && (dist - h.t) > DRT_EPS) return true; }
+    if (c.kind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, c.idx, r, time, h) && (dist - h.t) > DRT_EPS) return 1; }
     else {
       const FInstance I = S.instances[c.idx];
-      if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, I.baseIdx, r, time, h) && (dist - h.t) > DRT_EPS) return true; }
-      else if (LVL == 1) { if (accelShadow<2>(S, I.baseKind, I.baseIdx, r, r, time, dist, tc)) return true; }
+      if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, I.baseIdx, r, time, h) && (dist - h.t) > DRT_EPS) return 1; }
+      else if constexpr (LVL == 1) {
+        if constexpr (!(F & TF_LITERAL1)) return -1;
+        else { const int got = accelShadow<F, 2>(S, I.baseKind, I.baseIdx, r, r, time, dist, tc); if (got != 0) return got; }
+      }
     }
   }
-  return false;
+  return 0;
 }
-template <int LVL>
-__device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc) {
+template <int F, int LVL>
+__device__ int accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc) {
+  constexpr bool LITERAL = (LVL == 1) ? ((F & TF_LITERAL1) != 0) : ((F & TF_LEVEL2) != 0);
+  constexpr bool NONLEAN = (LVL == 1) ? ((F & TF_NONLEAN) != 0) : ((F & TF_LEVEL2) != 0);
   const D3 inv = rayInv(trans);
   XfCache xc; xc.xf = -1;
-  if (kind == OK_LIST) return listShadow<LVL>(S, idx, _ray, trans, inv, time, dist, tc, xc);
+  if (kind == OK_LIST) return listShadow<F, LVL>(S, idx, _ray, trans, inv, time, dist, tc, xc);
   const FBvh& B = S.bvhs[idx];
   if (S.accelMode != 0 && B.fast != 0) {                              // any-hit does not depend on the visiting order
     const Ray r = xfRay(_ray, S.xforms[B.triXform].inv);
     const bool one = sameRay(trans, r);
 #if DRT_LEAN
-    if (regularDir(trans.a)) return one ? leanShadow<true>(S, B, trans.o, trans.a, r.o, r.d, dist, tc) : leanShadow<false>(S, B, trans.o, trans.a, r.o, r.d, dist, tc);
+    if (regularDir(trans.a)) {
+      if constexpr (F == TF_ALL) {
+        const int got = one ? leanShadow<true, DRT_FSTACK>(S, B, trans.o, trans.a, r.o, r.d, dist, tc) : leanShadow<false, DRT_FSTACK>(S, B, trans.o, trans.a, r.o, r.d, dist, tc);
+        if (got < 0) { flagError(1u); return 0; }
+        return got;
+      } else if constexpr ((F & TF_LITERAL1) != 0) return leanShadow<false, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, dist, tc);
+      else { if (!one) return -1; return leanShadow<true, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, dist, tc); }
+    }
 #endif
-    return one ? fastShadow<true>(S, B, trans, r, dist, tc) : fastShadow<false>(S, B, trans, r, dist, tc);
+    if constexpr (!NONLEAN) return -1;
+    else return (one ? fastShadow<true>(S, B, trans, r, dist, tc) : fastShadow<false>(S, B, trans, r, dist, tc)) ? 1 : 0;
   }
+  if constexpr (!LITERAL) return -1;
+  else {
   int32_t stack[DRT_STACK]; int sp = 0; int32_t node = B.root;
   while (true) {
-    if (node < 0) { if (listShadow<LVL>(S, ~node, _ray, trans, inv, time, dist, tc, xc)) return true; }
+    if (node < 0) { const int got = listShadow<F, LVL>(S, ~node, _ray, trans, inv, time, dist, tc, xc); if (got != 0) return got; }
     else {
       const FNode& N = S.nodes[node];
       if (tc) tc->box += 2;
@@ -767,11 +821,13 @@ __device__ bool accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const
       if (hl) { if (hr) { if (sp < DRT_STACK) stack[sp++] = N.right; else flagError(1u); } node = N.left; continue; }
       if (hr) { node = N.right; continue; }
     }
-    if (sp == 0) return false;
+    if (sp == 0) return 0;
     node = stack[--sp];
   }
+  }
 }
-__device__ __forceinline__ bool anyHit(const DScene& S, Ray& ray, double time, double dist, TraceCounters* tc) {
+template <int F>
+__device__ __forceinline__ int anyHitT(const DScene& S, Ray& ray, double time, double dist, TraceCounters* tc) {
   Ray tr; int trXf = -1;
   for (int i = 0; i < S.g.numTop; ++i) {
     const FObjRef o = S.top[i];
@@ -780,16 +836,17 @@ __device__ __forceinline__ bool anyHit(const DScene& S, Ray& ray, double time, d
     if (o.kind == OK_PRIM) {
       if (tc) ++tc->prim;
       const int triIdx = (S.accelMode != 0) ? S.prims[o.idx].pad0 : -1;
-      if (triIdx >= 0) { int32_t rank; if (leanTri(S.tris + triIdx, tr.o.x, tr.o.y, tr.o.z, tr.d.x, tr.d.y, tr.d.z, DRT_DMAX, h.t, h.state, rank) && (dist - h.t) > DRT_EPS) return true; }
-      else if (primTest(S, o.idx, tr, time, h) && (dist - h.t) > DRT_EPS) return true;
+      if (triIdx >= 0) { int32_t rank; if (leanTri(S.tris + triIdx, tr.o.x, tr.o.y, tr.o.z, tr.d.x, tr.d.y, tr.d.z, DRT_DMAX, h.t, h.state, rank) && (dist - h.t) > DRT_EPS) return 1; }
+      else if (primTest(S, o.idx, tr, time, h) && (dist - h.t) > DRT_EPS) return 1;
     }
     else if (o.kind == OK_INSTANCE) {
       const FInstance I = S.instances[o.idx];
-      if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, I.baseIdx, tr, time, h) && (dist - h.t) > DRT_EPS) return true; }
-      else if (accelShadow<1>(S, I.baseKind, I.baseIdx, tr, tr, time, dist, tc)) return true;
-    } else if (accelShadow<1>(S, o.kind, o.idx, ray, tr, time, dist, tc)) return true;
+      if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, I.baseIdx, tr, time, h) && (dist - h.t) > DRT_EPS) return 1; }
+      else { const int got = accelShadow<F, 1>(S, I.baseKind, I.baseIdx, tr, tr, time, dist, tc); if (got != 0) return got; }
+    } else { const int got = accelShadow<F, 1>(S, o.kind, o.idx, ray, tr, time, dist, tc); if (got != 0) return got; }
   }
-  return false;
+  return 0;
 }
+__device__ __forceinline__ bool anyHit(const DScene& S, Ray& ray, double time, double dist, TraceCounters* tc) { return anyHitT<TF_ALL>(S, ray, time, dist, tc) > 0; }
 
 }  // namespace drt

@@ -32,6 +32,7 @@ static void toStats(const RenderStats& r, drt_stats* s) {
   s->rays_primary = r.primary; s->rays_shadow = r.shadow; s->rays_reflect = r.reflect; s->rays_refract = r.refract; s->rays_photon = r.photonSeg;
   s->box_tests = r.boxTests; s->prim_tests = r.primTests; s->photons_stored = r.photonsStored; s->kernel_launches = r.kernelLaunches; s->box_tests_closest = r.boxTestsClosest; s->prim_tests_closest = r.primTestsClosest;
   s->ms_trace = r.msTrace; s->ms_shade = r.msShade; s->ms_light = r.msLight; s->ms_other = r.msOther; s->ms_total = r.msTotal;
+  s->rays_deferred = r.deferred; s->frame_retries = r.retries; s->host_syncs = r.hostSyncs;
 }
 #define NEED_DEV(ctx) if ((ctx) && !(ctx)->renderer) { (ctx)->err = "host-only context: no CUDA device, and this library has no CPU fallback"; return DRT_ERR_NO_DEVICE; }
 #define GUARD(ctx, body, code) if (!(ctx)) return DRT_ERR_BAD_ARG; try { body; return DRT_OK; } catch (std::exception& e) { (ctx)->err = e.what(); return code; }
@@ -67,7 +68,7 @@ int drt_scene_finalize(drt_ctx* ctx, int32_t accel_mode) {
     ctx->scene->finalize();
     if (ctx->renderer) { ctx->renderer->setTraceMode(accel_mode); ctx->renderer->upload(*ctx->scene); ctx->finalized = true; } }, DRT_ERR_SCENE)
 }
-int drt_scene_reupload(drt_ctx* ctx) { NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized) throw std::runtime_error("scene not finalized"); ctx->renderer->upload(*ctx->scene); }, DRT_ERR_STATE) }
+int drt_scene_reupload(drt_ctx* ctx) { NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized) throw std::runtime_error("scene not finalized"); ctx->renderer->upload(*ctx->scene, true); }, DRT_ERR_STATE) }
 int drt_accel_info(drt_ctx* ctx, double* out4) { NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized || !out4) throw std::runtime_error("scene not finalized"); ctx->renderer->accelInfo(out4); }, DRT_ERR_STATE) }
 int drt_scene_counts(drt_ctx* ctx, int64_t* o) {
   GUARD(ctx, { if (!o) throw std::runtime_error("null output"); ctx->scene->finalize(); const HostScene& s = *ctx->scene; std::memset(o, 0, 8 * sizeof(int64_t));

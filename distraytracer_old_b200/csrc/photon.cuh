@@ -351,9 +351,14 @@ __device__ __forceinline__ void phMakePlan(const DScene& S, D3 p, uint32_t coars
   if (!inside) return;
   // expected share of a cube's photons that lie inside the sphere of radius s fine cells (surface distribution): pi s^2 / (2s+1)^2
   const double frac[4] = {0.0, 0.349, 0.503, 0.577};
-  for (int s = 1; s <= 3; ++s) if ((double)phCountFineCube(S, f, s) * frac[s] >= 1.25 * K) {
-    pl.fineHalf = s; for (int k = 0; k < 3; ++k) { pl.c[k] = f[k]; pl.h[k] = s; }
-    const double rad = s * cf * (1.0 - 1e-6); pl.r2 = rad * rad; return;       // 1e-6: a photon's own fine index is a rounded quotient
+  for (int s = 1; s <= 3; ++s) {
+    const double rad = s * cf * (1.0 - 1e-6);                                  // 1e-6: a photon's own fine index is a rounded quotient
+    if (!(rad * rad <= S.g.phMaxDist2)) return;                                // never search beyond the scene's radius (find_near requires d^2 < r^2): when the
+                                                                               // grid had to double its cell size the fine cells are wider than r/4 and the plan does not apply
+    if ((double)phCountFineCube(S, f, s) * frac[s] >= 1.25 * K) {
+      pl.fineHalf = s; for (int k = 0; k < 3; ++k) { pl.c[k] = f[k]; pl.h[k] = s; }
+      pl.r2 = rad * rad; return;
+    }
   }
 }
 // ---- one query per lane, three tiers by the number of photons in the candidate cells (all exact):
@@ -459,24 +464,29 @@ __device__ __forceinline__ void phApply(const DScene& S, int shIdx, const double
   if (sh.flags & SF_IS_CAUSTIC_PHTN) { l[0] = l[0] + irr.x; l[1] = l[1] + irr.y; l[2] = l[2] + irr.z; }
   else { l[0] = l[0] + sh.diff[0] * irr.x; l[1] = l[1] + sh.diff[1] * irr.y; l[2] = l[2] + sh.diff[2] * irr.z; }
 }
-__global__ void __launch_bounds__(128) k_photon_gather_lane(const __grid_constant__ DScene S, long long n, SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes) {
+__global__ void __launch_bounds__(128) k_photon_gather_lane(const __grid_constant__ DScene S, Wave w, SurfRec* __restrict__ surf, NodeRec* __restrict__ nodesBase, const Counters* ctr) {
   __shared__ PhLaneShared sm;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
-  const SurfRec s = surf[i]; if (!s.valid) return;
-  const FShader& sh = S.shaders[s.shader];
-  const bool needs = !(sh.flags & SF_SIMPLE) && (sh.KRefl == 0.0) && (sh.flags & SF_USE_PHOTON);
-  double sum[3], dmax2; const bool pending = phLaneTiers(S, needs, d3(s.loc[0], s.loc[1], s.loc[2]), sm, sum, dmax2, nullptr);
-  surf[i].pad = pending ? 1 : 0;
-  if (needs && !pending) phApply(S, s.shader, sum, dmax2, nodes[i].local);
+  const long long n = waveCount(w, ctr); NodeRec* __restrict__ nodes = nodesBase + ((w.level == 0) ? 0 : waveNodeOffset(ctr, w.level));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const SurfRec s = surf[i]; if (!s.valid) continue;
+    const FShader& sh = S.shaders[s.shader];
+    const bool needs = !(sh.flags & SF_SIMPLE) && (sh.KRefl == 0.0) && (sh.flags & SF_USE_PHOTON);
+    double sum[3], dmax2; const bool pending = phLaneTiers(S, needs, d3(s.loc[0], s.loc[1], s.loc[2]), sm, sum, dmax2, nullptr);
+    surf[i].pad = pending ? 1 : 0;
+    if (needs && !pending) phApply(S, s.shader, sum, dmax2, nodes[i].local);
+  }
 }
-__global__ void __launch_bounds__(128) k_photon_gather_warp(const __grid_constant__ DScene S, long long n, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes) {
+__global__ void __launch_bounds__(128) k_photon_gather_warp(const __grid_constant__ DScene S, Wave w, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodesBase, const Counters* ctr) {
   __shared__ PhWarpTierShared sm;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  bool pending = false; D3 loc = d3(0, 0, 0); int shIdx = -1;
-  if (i < n) { pending = surf[i].valid && surf[i].pad == 1; if (pending) { shIdx = surf[i].shader; loc = d3(surf[i].loc[0], surf[i].loc[1], surf[i].loc[2]); } }
-  if (!__any_sync(0xffffffffu, pending)) return;
-  double sum[3], dmax2; phWarpTier(S, pending, loc, sm, sum, dmax2, nullptr);
-  if (pending) phApply(S, shIdx, sum, dmax2, nodes[i].local);
+  const long long n = waveCount(w, ctr); NodeRec* __restrict__ nodes = nodesBase + ((w.level == 0) ? 0 : waveNodeOffset(ctr, w.level));
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
+    const long long i = base + threadIdx.x;
+    bool pending = false; D3 loc = d3(0, 0, 0); int shIdx = -1;
+    if (i < n) { pending = surf[i].valid && surf[i].pad == 1; if (pending) { shIdx = surf[i].shader; loc = d3(surf[i].loc[0], surf[i].loc[1], surf[i].loc[2]); } }
+    if (!__any_sync(0xffffffffu, pending)) continue;
+    double sum[3], dmax2; phWarpTier(S, pending, loc, sm, sum, dmax2, nullptr);
+    if (pending) phApply(S, shIdx, sum, dmax2, nodes[i].local);
+  }
 }
 
 // parity probe: the same routines at explicit points, one lane per point: out = {sum r,g,b, dmax2, tier taken}

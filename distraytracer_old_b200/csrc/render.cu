@@ -35,8 +35,25 @@ struct PixMap { long long chunkPix, totalPix; int world, rank; };
 __host__ __device__ __forceinline__ long long absPixel(const PixMap& m, long long p) { return ((p / m.chunkPix) * m.world + m.rank) * m.chunkPix + (p % m.chunkPix); }
 
 // primaryS / shadowS: the two counters every warp bumps are spread over 64 slots (block index & 63) and summed on the host -- one address for
-// four million warps per frame showed up as 13 % of k_shade's stall samples
-struct Counters { unsigned long long primary, shadow, reflect, refract, box, prim, nextCount, boxC, primC, pad; unsigned long long primaryS[64], shadowS[64]; };
+// four million warps per frame showed up as 13 % of k_shade's stall samples.
+// The first block accumulates over a whole render call; everything from `levelCount` on is the per-batch wavefront state (zeroed per batch):
+// the number of rays of every bounce level and the lengths of the deferral lists live on the DEVICE, so the host never waits for a level.
+#define DRT_MAX_LEVELS 16
+struct Counters {
+  unsigned long long primary, shadow, reflect, refract, box, prim, nextCount, boxC, primC, pad; unsigned long long primaryS[64], shadowS[64];
+  unsigned long long deferredTotal, maxLevel;
+  unsigned long long levelCount[DRT_MAX_LEVELS + 1], deferTrace[DRT_MAX_LEVELS + 1], deferLight[DRT_MAX_LEVELS + 1];
+};
+// wavefront geometry of one launch: level 0 holds n0 primary rays generated on the fly (no ray records), level L >= 1 holds levelCount[L]
+// rays that level L-1's surface pass enqueued.  Node records of all levels of a batch are contiguous: level L starts at sum(levelCount[0..L-1]).
+struct Wave { long long n0, rayCap, nodeCap; int level, launchedLevels; };
+__device__ __forceinline__ long long waveCount(const Wave& w, const Counters* ctr) {
+  if (w.level == 0) return w.n0;
+  const long long c = (long long)ctr->levelCount[w.level]; return c < w.rayCap ? c : w.rayCap;
+}
+__device__ __forceinline__ long long waveNodeOffset(const Counters* ctr, int level) {
+  long long off = 0; for (int l = 0; l < level; ++l) off += (long long)ctr->levelCount[l]; return off;
+}
 
 // 16-byte-granular streaming (evict-first) copies of the 16-byte-aligned wavefront records
 template <class T> __device__ __forceinline__ void streamLoad(T* dst, const T* src) {
@@ -55,14 +72,23 @@ __device__ __forceinline__ void warpAdd(unsigned long long* dst, unsigned long l
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
 }
+// warp-aggregated append of the calling lanes' indices to a deferral list
+__device__ __forceinline__ void deferAppend(bool doIt, uint32_t idx, unsigned long long* counter, uint32_t* __restrict__ list) {
+  const unsigned m = __ballot_sync(0xffffffffu, doIt); if (!m) return;
+  const unsigned lane = threadIdx.x & 31; const int leader = __ffs(m) - 1;
+  unsigned long long base = 0; if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (doIt) list[base + __popc(m & ((1u << lane) - 1u))] = idx;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DScene S, PixMap pm, long long pix0, long long nRays, RayRec* __restrict__ rays, NodeRec* __restrict__ nodes) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= nRays) return;
+// primary ray of (pixel, sample) index i of the batch -- generated where it is needed (k_trace and k_shade at level 0) instead of being
+// written to and re-read from HBM
+__device__ __forceinline__ void primaryRay(const DScene& S, const PixMap& pm, long long pix0, long long i, RayRec& r) {
   const FGlobals& g = S.g; int spp = g.spp < 1 ? 1 : g.spp;
   long long pix = absPixel(pm, pix0 + i / spp); uint32_t smp = (uint32_t)(i % spp);
   int row = (int)(pix / g.cols), col = (int)(pix % g.cols);
-  RayRec r; r.kt0 = 1; r.kt1 = 1; r.ka = (uint32_t)pix; r.kb = smp; r.kc = 1; r.stream = STREAM_PIXEL; r.gen = 0; r.valid = 1; r.pad[0] = r.pad[1] = 0;
+  r.kt0 = 1; r.kt1 = 1; r.ka = (uint32_t)pix; r.kb = smp; r.kc = 1; r.stream = STREAM_PIXEL; r.gen = 0; r.valid = 1; r.pad[0] = r.pad[1] = 0;
   D3 o = d3(g.eye[0], g.eye[1], g.eye[2]), d = d3(0, 0, -1);
   auto U = [&](uint32_t dim) { return philoxU01(g.seed, STREAM_PIXEL, (uint32_t)pix, smp, 1, dim); };
   if (g.spp < 1 || pix >= pm.totalPix) r.valid = 0;     // rays_per_pixel 0: the reference averages nothing (0/0 -> NaN -> 0); ragged last chunk
@@ -94,10 +120,6 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DScene S
   }
   d = norm3(d);
   r.o[0] = o.x; r.o[1] = o.y; r.o[2] = o.z; r.d[0] = d.x; r.d[1] = d.y; r.d[2] = d.z;
-  rays[i] = r;
-  NodeRec n; n.parent = -1; n.slot = 0; n.pad[0] = n.pad[1] = 0;
-  for (int k = 0; k < 3; ++k) { n.local[k] = 0; n.cA[k] = 0; n.cB[k] = 0; n.w[k] = 1; }
-  nodes[i] = n;
 }
 
 __device__ __forceinline__ double rayTime(const DScene& S, uint32_t stream, uint32_t a, uint32_t b, uint32_t c, uint32_t dim) {
@@ -110,19 +132,38 @@ __device__ __forceinline__ double rayTime(const DScene& S, uint32_t stream, uint
 #ifndef DRT_LIGHT_MINBLOCKS
 #define DRT_LIGHT_MINBLOCKS 6
 #endif
-template <bool COUNT>
-__global__ void __launch_bounds__(128, DRT_TRACE_MINBLOCKS) k_trace(const __grid_constant__ DScene S, long long n, const RayRec* __restrict__ rays, Hit* __restrict__ hits, Counters* ctr) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+#ifndef DRT_LTRACE_MINBLOCKS
+#define DRT_LTRACE_MINBLOCKS 6       // lean variants (F != TF_ALL)
+#endif
+#ifndef DRT_LLIGHT_MINBLOCKS
+#define DRT_LLIGHT_MINBLOCKS 6
+#endif
+// Closest-hit pass of one level.  F = compile-time feature set (dev_isect.cuh): the lean variants defer what they cannot serve to `deferOut`;
+// the generic variant (TF_ALL) serves everything and is also the fix-up pass over such a list (`work` != null: ray indices to trace).
+// rays == null: level 0, the primary ray is generated from the index.
+template <bool COUNT, int F>
+__global__ void __launch_bounds__(128, (F == TF_ALL) ? DRT_TRACE_MINBLOCKS : DRT_LTRACE_MINBLOCKS)
+k_trace(const __grid_constant__ DScene S, Wave w, PixMap pm, long long pix0, const RayRec* __restrict__ rays, Hit* __restrict__ hits, Counters* ctr, const uint32_t* __restrict__ work, uint32_t* __restrict__ deferOut) {
+  const long long n = work ? (long long)ctr->deferTrace[w.level] : waveCount(w, ctr);
+  if (w.level == 0 && !work && blockIdx.x == 0 && threadIdx.x == 0) ctr->levelCount[0] = (unsigned long long)w.n0;
+  if (work && n > 0 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->deferredTotal, (unsigned long long)n);
   TraceCounters tc; tc.box = 0; tc.prim = 0;
-  if (i < n) {
-    // the ray / hit records are pure streams (read once, written once): evict-first loads and stores keep them from pushing the scene and the
-    // local-memory traversal state out of L2
-    RayRec r; streamLoad(&r, rays + i); Hit h; hitReset(h);
-    if (r.valid) {
-      Ray ray = makeRay(d3(r.o[0], r.o[1], r.o[2]), d3(r.d[0], r.d[1], r.d[2]));
-      closestHit(S, ray, rayTime(S, r.stream, r.ka, r.kb, r.kc, r.stream == STREAM_PIXEL ? DIM_TIME : 0xFFFFu), h, COUNT ? &tc : nullptr);
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
+    long long i = base + threadIdx.x; bool defer = false;
+    if (i < n) {
+      if (work) i = work[i];
+      // the ray / hit records are pure streams (read once, written once): evict-first loads and stores keep them from pushing the scene and the
+      // local-memory traversal state out of L2
+      RayRec r; if (rays) streamLoad(&r, rays + i); else primaryRay(S, pm, pix0, i, r);
+      Hit h; hitReset(h);
+      if (r.valid) {
+        Ray ray = makeRay(d3(r.o[0], r.o[1], r.o[2]), d3(r.d[0], r.d[1], r.d[2]));
+        const int got = closestHitT<F>(S, ray, rayTime(S, r.stream, r.ka, r.kb, r.kc, r.stream == STREAM_PIXEL ? DIM_TIME : 0xFFFFu), h, COUNT ? &tc : nullptr);
+        if (F != TF_ALL && got < 0) { defer = true; hitReset(h); }
+      }
+      if (!defer) streamStore(hits + i, &h);
     }
-    streamStore(hits + i, &h);
+    if (F != TF_ALL) deferAppend(defer, (uint32_t)i, &ctr->deferTrace[w.level], deferOut);
   }
   if (COUNT) { warpAdd(&ctr->box, tc.box); warpAdd(&ctr->prim, tc.prim); warpAdd(&ctr->boxC, tc.box); warpAdd(&ctr->primC, tc.prim); }
 }
@@ -149,24 +190,32 @@ __device__ inline D3 skyColor(const DScene& S, D3 o, D3 d) {
   return colorOfArgb(S.texels[im.offset + idx]);
 }
 
-// Surface pass. One thread per ray of the level; children go to the next level's queue.
+// Surface pass. One thread per ray of the level; children go to the next level's queue (its length lives on the device: levelCount[level+1]).
+// rays == null: level 0 -- the primary ray is regenerated from the index and the node record is written whole (no k_raygen pass).
 #ifndef DRT_SHADE_MINBLOCKS
 #define DRT_SHADE_MINBLOCKS 4
 #endif
-__global__ void __launch_bounds__(128, DRT_SHADE_MINBLOCKS) k_shade(const __grid_constant__ DScene S, long long n, const RayRec* __restrict__ rays, const Hit* __restrict__ hits,
-                                               SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, RayRec* __restrict__ nextRays, NodeRec* __restrict__ nextNodes,
-                                               Counters* ctr, long long nextCap) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128, DRT_SHADE_MINBLOCKS) k_shade(const __grid_constant__ DScene S, Wave w, PixMap pm, long long pix0, const RayRec* __restrict__ rays, const Hit* __restrict__ hits,
+                                               SurfRec* __restrict__ surf, NodeRec* __restrict__ nodesBase, RayRec* __restrict__ nextRays, Counters* ctr) {
+  const long long n = waveCount(w, ctr);
+  const long long off = (w.level == 0) ? 0 : waveNodeOffset(ctr, w.level), offNext = off + ((w.level == 0) ? w.n0 : (long long)ctr->levelCount[w.level]);
+  NodeRec* __restrict__ nodes = nodesBase + off; NodeRec* __restrict__ nextNodes = nodesBase + offNext;
+  const long long nextCap = (w.nodeCap - offNext) < w.rayCap ? (w.nodeCap - offNext) : w.rayCap;
+  const unsigned lane = threadIdx.x & 31;
+  unsigned long long cntPrimary = 0, cntRefl = 0, cntRefr = 0;
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
+  const long long i = base + threadIdx.x;
   // up to two children per hit: A = refraction (slot 1), B = reflection (slot 2). Kept in named registers (no dynamically indexed local arrays)
   bool hasA = false, hasB = false; D3 dirA = d3(0, 0, 0), wA = dirA, dirB = dirA, wB = dirA, orgC = dirA; double ktA0 = 1, ktA1 = 1, ktB0 = 1, ktB1 = 1;
   uint32_t cka = 0, ckb = 0, ckc = 0, cstream = 0; int32_t cgen = 0;
-  unsigned long long cPrimary = 0, cRefl = 0, cRefr = 0;
+  bool cPrimary = false, cRefl = false, cRefr = false;
   if (i < n) {
-    const RayRec r = rays[i]; const Hit h = hits[i];
+    RayRec r; if (rays) r = rays[i]; else primaryRay(S, pm, pix0, i, r);
+    const Hit h = hits[i];
     SurfRec s; s.valid = 0; s.shader = -1; s.ka = r.ka; s.kb = r.kb; s.kc = r.kc; s.stream = r.stream; s.gen = r.gen; s.pad = 0;
     D3 local = d3(0, 0, 0);
     if (r.valid) {
-      if (r.gen == 0) cPrimary = 1;
+      if (r.gen == 0) cPrimary = true;
       if (h.prim < 0) {
         if (S.g.hasSky) local = skyColor(S, d3(r.o[0], r.o[1], r.o[2]), d3(r.d[0], r.d[1], r.d[2]));
         else local = d3(S.g.bg[0], S.g.bg[1], S.g.bg[2]);
@@ -185,95 +234,115 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MINBLOCKS) k_shade(const __grid
         // secondary rays (leave room for the shadow generation: gen < numRays - 2)
         if ((r.gen < S.g.numRays - 2) && (sh.flags & SF_HAS_CAUSTIC)) {
           orgC = fwd; cka = r.ka; ckb = r.kb; ckc = r.kc; cstream = r.stream; cgen = r.gen + 1;
-          auto child = [&](int slot, D3 dir, D3 w, double kt0, double kt1) {
-            if (slot == 1) { hasA = true; dirA = norm3(dir); wA = w; ktA0 = kt0; ktA1 = kt1; } else { hasB = true; dirB = norm3(dir); wB = w; ktB0 = kt0; ktB1 = kt1; }
+          auto child = [&](int slot, D3 dir, D3 wgt, double kt0, double kt1) {
+            if (slot == 1) { hasA = true; dirA = norm3(dir); wA = wgt; ktA0 = kt0; ktA1 = kt1; } else { hasB = true; dirB = norm3(dir); wB = wgt; ktB0 = kt0; ktB1 = kt1; }
           };
           D3 perm = d3(sh.perm[0], sh.perm[1], sh.perm[2]);
           bool trans = simple ? (sh.KTrans > 0) : ((sh.KTrans > 0) || (sh.currPerm > 0.0));
           if (trans) {
             Fres f = simple ? fresnel(h.rawDir, nrm, sh.currPerm, r.kt1) : fresnel(h.rawDir, nrm, sh.KTrans, r.kt0);
             const double thr = simple ? 0.0 : DRT_EPS;
-            if (f.oneM > thr) { D3 w = simple ? d3(f.oneM * sh.KTrans, f.oneM * sh.KTrans, f.oneM * sh.KTrans) : d3((f.oneM) * perm.x, (f.oneM) * perm.y, (f.oneM) * perm.z);
-              child(1, refractDir(f), w, sh.KTrans, sh.currPerm); cRefr = 1; }
+            if (f.oneM > thr) { D3 wgt = simple ? d3(f.oneM * sh.KTrans, f.oneM * sh.KTrans, f.oneM * sh.KTrans) : d3((f.oneM) * perm.x, (f.oneM) * perm.y, (f.oneM) * perm.z);
+              child(1, refractDir(f), wgt, sh.KTrans, sh.currPerm); cRefr = true; }
             if (f.ratio > thr) { D3 rd = scale3(reflDir(f.back, f.N), f.mult);
-              D3 w = simple ? d3(f.ratio * sh.KRefl, f.ratio * sh.KRefl, f.ratio * sh.KRefl) : d3((f.ratio) * perm.x, (f.ratio) * perm.y, (f.ratio) * perm.z);
-              if (simple) child(2, rd, w, 1, 1); else child(2, rd, w, sh.KTrans, sh.currPerm); cRefl = 1; }
+              D3 wgt = simple ? d3(f.ratio * sh.KRefl, f.ratio * sh.KRefl, f.ratio * sh.KRefl) : d3((f.ratio) * perm.x, (f.ratio) * perm.y, (f.ratio) * perm.z);
+              if (simple) child(2, rd, wgt, 1, 1); else child(2, rd, wgt, sh.KTrans, sh.currPerm); cRefl = true; }
           } else if (sh.KRefl > 0.0) {
             D3 back = scale3(h.rawDir, -1); D3 rd = reflDir(back, nrm);
-            if (dot3(rd, nrm) >= 0) { child(2, rd, d3(sh.kreflClr[0], sh.kreflClr[1], sh.kreflClr[2]), 1, 1); cRefl = 1; }
+            if (dot3(rd, nrm) >= 0) { child(2, rd, d3(sh.kreflClr[0], sh.kreflClr[1], sh.kreflClr[2]), 1, 1); cRefl = true; }
           }
         }
       }
     }
     surf[i] = s;
-    nodes[i].local[0] = local.x; nodes[i].local[1] = local.y; nodes[i].local[2] = local.z;
+    if (rays) { nodes[i].local[0] = local.x; nodes[i].local[1] = local.y; nodes[i].local[2] = local.z; }
+    else { NodeRec nd; nd.parent = -1; nd.slot = 0; nd.pad[0] = nd.pad[1] = 0; nd.local[0] = local.x; nd.local[1] = local.y; nd.local[2] = local.z;
+      for (int k = 0; k < 3; ++k) { nd.cA[k] = 0; nd.cB[k] = 0; nd.w[k] = 1; } nodes[i] = nd; }
   }
   // warp-aggregated compaction of the children into the next level's queue
-  unsigned lane = threadIdx.x & 31;
   const int nChild = (hasA ? 1 : 0) + (hasB ? 1 : 0);
   int incl = nChild;
   for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += v; }
   int total = __shfl_sync(0xffffffffu, incl, 31);
-  unsigned long long base = 0;
-  if (total > 0) { if (lane == 31) base = atomicAdd(&ctr->nextCount, (unsigned long long)total); base = __shfl_sync(0xffffffffu, base, 31); }
-  long long at = (long long)base + (incl - nChild);
-  auto emit = [&](long long pos, int slot, D3 dn, D3 w, double kt0, double kt1) {
+  unsigned long long qbase = 0;
+  if (total > 0) {
+    if (lane == 31) { qbase = atomicAdd(&ctr->levelCount[w.level + 1], (unsigned long long)total);
+      if (ctr->maxLevel < (unsigned long long)(w.level + 1)) atomicMax(&ctr->maxLevel, (unsigned long long)(w.level + 1));
+      if (w.level + 1 >= w.launchedLevels) flagError(4u);                               // deeper than the levels this call launched: the host re-renders with full depth
+      if ((long long)(qbase + total) > nextCap) flagError(2u); }                          // queue / node pool exhausted: the host re-renders with smaller batches
+    qbase = __shfl_sync(0xffffffffu, qbase, 31);
+  }
+  long long at = (long long)qbase + (incl - nChild);
+  auto emit = [&](long long pos, int slot, D3 dn, D3 wgt, double kt0, double kt1) {
     if (pos >= nextCap) return;
     RayRec c; c.o[0] = orgC.x; c.o[1] = orgC.y; c.o[2] = orgC.z; c.d[0] = dn.x; c.d[1] = dn.y; c.d[2] = dn.z; c.kt0 = kt0; c.kt1 = kt1;
     c.ka = cka; c.kb = ckb; c.kc = ckc * 2 + (slot == 1 ? 1 : 0); c.stream = cstream; c.gen = cgen; c.valid = 1; c.pad[0] = c.pad[1] = 0;
-    NodeRec nn; nn.parent = (int32_t)i; nn.slot = slot; nn.pad[0] = nn.pad[1] = 0; nn.w[0] = w.x; nn.w[1] = w.y; nn.w[2] = w.z;
+    NodeRec nn; nn.parent = (int32_t)i; nn.slot = slot; nn.pad[0] = nn.pad[1] = 0; nn.w[0] = wgt.x; nn.w[1] = wgt.y; nn.w[2] = wgt.z;
     for (int k = 0; k < 3; ++k) { nn.local[k] = 0; nn.cA[k] = 0; nn.cB[k] = 0; }
     nextRays[pos] = c; nextNodes[pos] = nn;
   };
   if (hasA) emit(at, 1, dirA, wA, ktA0, ktA1);
   if (hasB) emit(at + (hasA ? 1 : 0), 2, dirB, wB, ktB0, ktB1);
   // 0/1 flags: one ballot + popc per counter instead of a 64-bit shuffle tree
-  { const unsigned bp = __ballot_sync(0xffffffffu, cPrimary != 0), bl = __ballot_sync(0xffffffffu, cRefl != 0), br = __ballot_sync(0xffffffffu, cRefr != 0);
-    if (lane == 0) { if (bp) atomicAdd(&ctr->primaryS[blockIdx.x & 63], (unsigned long long)__popc(bp)); if (bl) atomicAdd(&ctr->reflect, (unsigned long long)__popc(bl)); if (br) atomicAdd(&ctr->refract, (unsigned long long)__popc(br)); } }
+  cntPrimary += __popc(__ballot_sync(0xffffffffu, cPrimary)); cntRefl += __popc(__ballot_sync(0xffffffffu, cRefl)); cntRefr += __popc(__ballot_sync(0xffffffffu, cRefr));
+  }
+  if (lane == 0) { if (cntPrimary) atomicAdd(&ctr->primaryS[blockIdx.x & 63], cntPrimary); if (cntRefl) atomicAdd(&ctr->reflect, cntRefl); if (cntRefr) atomicAdd(&ctr->refract, cntRefr); }
 }
 
 // Light pass: literal calcShadowColor, one thread per shaded hit, lights in list order, shadow rays traced in-thread.
-template <bool COUNT>
-__global__ void __launch_bounds__(128, DRT_LIGHT_MINBLOCKS) k_light(const __grid_constant__ DScene S, long long n, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodes, Counters* ctr) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// F / work / deferOut as in k_trace: a lean variant that meets a shadow ray it cannot serve leaves the WHOLE record to the generic pass
+// (the record's light sum is formed by one thread in list order either way).
+template <bool COUNT, int F>
+__global__ void __launch_bounds__(128, (F == TF_ALL) ? DRT_LIGHT_MINBLOCKS : DRT_LLIGHT_MINBLOCKS)
+k_light(const __grid_constant__ DScene S, Wave w, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodesBase, Counters* ctr, const uint32_t* __restrict__ work, uint32_t* __restrict__ deferOut) {
+  const long long n = work ? (long long)ctr->deferLight[w.level] : waveCount(w, ctr);
+  NodeRec* __restrict__ nodes = nodesBase + ((w.level == 0) ? 0 : waveNodeOffset(ctr, w.level));
+  if (work && n > 0 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->deferredTotal, (unsigned long long)n);
   TraceCounters tc; tc.box = 0; tc.prim = 0; unsigned long long cShadow = 0;
-  if (i < n) {
-    const SurfRec s = surf[i];
-    if (s.valid) {
-      const FShader sh = S.shaders[s.shader];
-      D3 hitLoc = d3(s.loc[0], s.loc[1], s.loc[2]), N = d3(s.n[0], s.n[1], s.n[2]), rawDir = d3(s.rawDir[0], s.rawDir[1], s.rawDir[2]);
-      double r = 0, g = 0, b = 0;
-      for (int li = 0; li < S.g.numLights; ++li) {
-        const FLight L = S.lights[li]; const FXform& LX = S.xforms[L.xform];
-        const uint32_t dim = DIM_LIGHT_BASE + DIM_LIGHT_STRIDE * li;
-        D3 lo = d3(L.origin[0], L.origin[1], L.origin[2]), orient = d3(L.orient[0], L.orient[1], L.orient[2]);
-        auto diskPos = [&](uint32_t d0) {           // myDiskLight.getRandomDiskPos (:251-258)
-          double ua = philoxU01(S.g.seed, s.stream, s.ka, s.kb, s.kc, d0), ur = philoxU01(S.g.seed, s.stream, s.ka, s.kb, s.kc, d0 + 1);
-          D3 tmp = norm3(rotAboutAxis(d3(L.tangent[0], L.tangent[1], L.tangent[2]), orient, urange(ua, 0, DRT_TWO_PI_F)));
-          return add3(scale3(tmp, urange(ur, 0, L.radius)), lo);
-        };
-        D3 target = (L.type == LT_DISK) ? diskPos(dim) : lo;
-        D3 lightNorm = norm3(sub3(xfPoint(LX.m, target), hitLoc));
-        Ray shadowRay = makeRay(hitLoc, lightNorm);
-        // light.intersectCheck: distance to the light's (re-sampled, untransformed) origin, penumbra factor
-        D3 dOrg = (L.type == LT_DISK) ? diskPos(dim + 2) : lo;
-        double t = sqrt(((hitLoc.x - dOrg.x) * (hitLoc.x - dOrg.x)) + ((hitLoc.y - dOrg.y) * (hitLoc.y - dOrg.y)) + ((hitLoc.z - dOrg.z) * (hitLoc.z - dOrg.z)));
-        double ltMult = 1;
-        if (L.type == LT_SPOT) { double angle = acos(-1 * dot3(lightNorm, orient)); ltMult = (angle < L.innerRad) ? 1 : (angle > L.outerRad) ? 0 : (L.outerRad - angle) / L.radDiff; }
-        if (ltMult == 0) continue;
-        ++cShadow;
-        double time = rayTime(S, s.stream, s.ka, s.kb, s.kc, dim + 4);
-        if (!anyHit(S, shadowRay, time, t, COUNT ? &tc : nullptr)) {
-          double ld = dot3(lightNorm, N) * ltMult;
-          if (ld > DRT_EPS) { r += s.tex[0] * L.color[0] * ld; g += s.tex[1] * L.color[1] * ld; b += s.tex[2] * L.color[2] * ld; }
-          if (sh.phong == 0) continue;
-          D3 hN = norm3(sub3(lightNorm, rawDir));
-          double hd = dot3(hN, N) * ltMult;
-          if (hd > DRT_EPS) { double ph = pow(hd * hd, sh.phong); r += sh.spec[0] * L.color[0] * ph; g += sh.spec[1] * L.color[1] * ph; b += sh.spec[2] * L.color[2] * ph; }
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
+    long long i = base + threadIdx.x; bool defer = false;
+    if (i < n) {
+      if (work) i = work[i];
+      const SurfRec s = surf[i];
+      if (s.valid) {
+        const FShader sh = S.shaders[s.shader];
+        D3 hitLoc = d3(s.loc[0], s.loc[1], s.loc[2]), N = d3(s.n[0], s.n[1], s.n[2]), rawDir = d3(s.rawDir[0], s.rawDir[1], s.rawDir[2]);
+        double r = 0, g = 0, b = 0; unsigned nShadow = 0;
+        for (int li = 0; li < S.g.numLights; ++li) {
+          const FLight L = S.lights[li]; const FXform& LX = S.xforms[L.xform];
+          const uint32_t dim = DIM_LIGHT_BASE + DIM_LIGHT_STRIDE * li;
+          D3 lo = d3(L.origin[0], L.origin[1], L.origin[2]), orient = d3(L.orient[0], L.orient[1], L.orient[2]);
+          auto diskPos = [&](uint32_t d0) {           // myDiskLight.getRandomDiskPos (:251-258)
+            double ua = philoxU01(S.g.seed, s.stream, s.ka, s.kb, s.kc, d0), ur = philoxU01(S.g.seed, s.stream, s.ka, s.kb, s.kc, d0 + 1);
+            D3 tmp = norm3(rotAboutAxis(d3(L.tangent[0], L.tangent[1], L.tangent[2]), orient, urange(ua, 0, DRT_TWO_PI_F)));
+            return add3(scale3(tmp, urange(ur, 0, L.radius)), lo);
+          };
+          D3 target = (L.type == LT_DISK) ? diskPos(dim) : lo;
+          D3 lightNorm = norm3(sub3(xfPoint(LX.m, target), hitLoc));
+          Ray shadowRay = makeRay(hitLoc, lightNorm);
+          // light.intersectCheck: distance to the light's (re-sampled, untransformed) origin, penumbra factor
+          D3 dOrg = (L.type == LT_DISK) ? diskPos(dim + 2) : lo;
+          double t = sqrt(((hitLoc.x - dOrg.x) * (hitLoc.x - dOrg.x)) + ((hitLoc.y - dOrg.y) * (hitLoc.y - dOrg.y)) + ((hitLoc.z - dOrg.z) * (hitLoc.z - dOrg.z)));
+          double ltMult = 1;
+          if (L.type == LT_SPOT) { double angle = acos(-1 * dot3(lightNorm, orient)); ltMult = (angle < L.innerRad) ? 1 : (angle > L.outerRad) ? 0 : (L.outerRad - angle) / L.radDiff; }
+          if (ltMult == 0) continue;
+          ++nShadow;
+          double time = rayTime(S, s.stream, s.ka, s.kb, s.kc, dim + 4);
+          const int occluded = anyHitT<F>(S, shadowRay, time, t, COUNT ? &tc : nullptr);
+          if (F != TF_ALL && occluded < 0) { defer = true; break; }
+          if (!occluded) {
+            double ld = dot3(lightNorm, N) * ltMult;
+            if (ld > DRT_EPS) { r += s.tex[0] * L.color[0] * ld; g += s.tex[1] * L.color[1] * ld; b += s.tex[2] * L.color[2] * ld; }
+            if (sh.phong == 0) continue;
+            D3 hN = norm3(sub3(lightNorm, rawDir));
+            double hd = dot3(hN, N) * ltMult;
+            if (hd > DRT_EPS) { double ph = pow(hd * hd, sh.phong); r += sh.spec[0] * L.color[0] * ph; g += sh.spec[1] * L.color[1] * ph; b += sh.spec[2] * L.color[2] * ph; }
+          }
         }
+        if (!defer) { cShadow += nShadow; nodes[i].local[0] += r; nodes[i].local[1] += g; nodes[i].local[2] += b; }
       }
-      nodes[i].local[0] += r; nodes[i].local[1] += g; nodes[i].local[2] += b;
     }
+    if (F != TF_ALL) deferAppend(defer, (uint32_t)i, &ctr->deferLight[w.level], deferOut);
   }
   warpAdd(&ctr->shadowS[blockIdx.x & 63], cShadow);
   if (COUNT) { warpAdd(&ctr->box, tc.box); warpAdd(&ctr->prim, tc.prim); }
@@ -282,12 +351,15 @@ __global__ void __launch_bounds__(128, DRT_LIGHT_MINBLOCKS) k_light(const __grid
 __device__ __forceinline__ D3 nodeTotal(const NodeRec& nd) {
   return clampColor1(d3(nd.local[0] + (nd.cA[0] + nd.cB[0]), nd.local[1] + (nd.cA[1] + nd.cB[1]), nd.local[2] + (nd.cA[2] + nd.cB[2])));
 }
-// level L -> level L-1: parent.slot = w (.) clamp1(total(child))
-__global__ void k_resolve(long long n, const NodeRec* __restrict__ lvl, NodeRec* __restrict__ parentLvl) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
-  const NodeRec nd = lvl[i]; D3 c = nodeTotal(nd);
-  double* dst = (nd.slot == 1) ? parentLvl[nd.parent].cA : parentLvl[nd.parent].cB;
-  dst[0] = nd.w[0] * c.x; dst[1] = nd.w[1] * c.y; dst[2] = nd.w[2] * c.z;
+// level L -> level L-1: parent.slot = w (.) clamp1(total(child)).  The level's length and position are read from the device counters.
+__global__ void k_resolve(Wave w, NodeRec* __restrict__ nodesBase, const Counters* ctr) {
+  const long long n = waveCount(w, ctr), off = waveNodeOffset(ctr, w.level), offP = off - (long long)ctr->levelCount[w.level - 1];
+  const NodeRec* __restrict__ lvl = nodesBase + off; NodeRec* __restrict__ parentLvl = nodesBase + offP;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const NodeRec nd = lvl[i]; D3 c = nodeTotal(nd);
+    double* dst = (nd.slot == 1) ? parentLvl[nd.parent].cA : parentLvl[nd.parent].cB;
+    dst[0] = nd.w[0] * c.x; dst[1] = nd.w[1] * c.y; dst[2] = nd.w[2] * c.z;
+  }
 }
 __global__ void k_finish(const __grid_constant__ DScene S, PixMap pm, long long pix0, long long nPix, const NodeRec* __restrict__ roots, const Hit* __restrict__ hits0, RenderOutputs out) {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (p >= nPix) return;
@@ -368,6 +440,13 @@ struct SceneArena {
 struct Renderer::Impl {
   DScene ds; SceneArena arena; DBuf<FNode> lbvhNodeBuf; DBuf<FTri> lbvhTriBuf; LbvhScratch lbvhScratch;
   DBuf<RayRec> rays[2]; DBuf<Hit> hits; DBuf<Hit> hits0; DBuf<SurfRec> surf; DBuf<NodeRec> nodes; Counters* ctr = nullptr; Counters* ctrHost = nullptr;
+  DBuf<uint32_t> deferT, deferL;                 // deferral lists of the lean trace / light kernels (ray indices of one level)
+  std::vector<cudaEvent_t> evPool;               // stage timing of a whole frame without a host sync per level
+  int shape = TF_ALL;                            // kernel variant the uploaded scene runs with (see chooseShape)
+  bool anySecondary = false;                     // some shader can spawn reflection / refraction rays
+  int depthHint = 0;                             // levels the last frame of this scene needed (0 = unknown: launch the full depth)
+  int numSMs = 148;
+  cudaEvent_t pev(size_t k) { while (evPool.size() <= k) { cudaEvent_t e; CK(cudaEventCreate(&e)); evPool.push_back(e); } return evPool[k]; }
   DBuf<int32_t> oArgb, oPrim, oInst; DBuf<double> oRgb, oT;
   cudaEvent_t ev[8];
   PhotonMap photons;
@@ -382,6 +461,7 @@ Renderer::Renderer(int device) : impl_(new Impl), device_(device) {
   if (const char* sl = getenv("DRT_STACK_LIMIT")) CK(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atol(sl)));     // debugging aid
   cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); stream_ = st;
   CK(cudaMalloc(&impl_->ctr, sizeof(Counters))); CK(cudaMallocHost(&impl_->ctrHost, sizeof(Counters)));
+  { cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, device)); impl_->numSMs = pr.multiProcessorCount; }
   for (auto& e2 : impl_->ev) CK(cudaEventCreate(&e2));
   std::memset(&impl_->ds, 0, sizeof(DScene)); std::memset(&g_, 0, sizeof(g_));
   static const unsigned char p[256] = {151,160,137,91,90,15,131,13,201,95,96,53,194,233,7,225,140,36,103,30,69,142,8,99,37,240,21,10,23,190,6,148,247,120,234,75,0,26,197,62,94,252,219,203,117,35,11,32,57,177,33,88,237,149,56,87,174,20,125,136,171,168,68,175,74,165,71,134,139,48,27,166,77,146,158,231,83,111,229,122,60,211,133,230,220,105,92,41,55,46,245,40,244,102,143,54,65,25,63,161,1,216,80,73,209,76,132,187,208,89,18,169,200,196,135,130,116,188,159,86,164,100,109,198,173,186,3,64,52,217,226,250,124,123,5,202,38,147,118,126,255,82,85,212,207,206,59,227,47,16,58,17,182,189,28,42,223,183,170,213,119,248,152,2,44,154,163,70,221,153,101,155,167,43,172,9,129,22,39,253,19,98,108,110,79,113,224,232,178,185,112,104,218,246,97,228,251,34,242,193,238,210,144,12,191,179,162,241,81,51,145,235,249,14,239,107,49,192,214,31,181,199,106,157,184,84,204,176,115,121,50,45,127,4,150,254,138,236,205,93,222,114,67,29,24,72,243,141,128,195,78,66,215,61,156,180};
@@ -393,13 +473,15 @@ Renderer::~Renderer() {
   impl_->arena.release(); impl_->lbvhNodeBuf.release(); impl_->lbvhTriBuf.release(); impl_->lbvhScratch.release();
   impl_->rays[0].release(); impl_->rays[1].release(); impl_->hits.release(); impl_->hits0.release(); impl_->surf.release(); impl_->nodes.release();
   impl_->oArgb.release(); impl_->oPrim.release(); impl_->oInst.release(); impl_->oRgb.release(); impl_->oT.release();
+  impl_->deferT.release(); impl_->deferL.release(); for (auto& e : impl_->evPool) cudaEventDestroy(e);
   impl_->photons.release();
   cudaFree(impl_->ctr); cudaFreeHost(impl_->ctrHost);
   for (auto& e : impl_->ev) cudaEventDestroy(e);
   cudaStreamDestroy((cudaStream_t)stream_); delete impl_;
 }
 
-void Renderer::upload(const HostScene& hs) {
+void Renderer::upload(const HostScene& hs, bool sameScene) {
+  keepDepthHint_ = sameScene;
   CK(cudaSetDevice(device_)); cudaStream_t st = (cudaStream_t)stream_;
   CK(cudaStreamSynchronize(st));
   // device-side nesting limits (see dev_isect.cuh): accel children are primitives or instances; an instanced accel holds primitives
@@ -441,6 +523,19 @@ void Renderer::upload(const HostScene& hs) {
     CK(cudaEventRecord(impl_->ev[7], st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError()); CK(cudaEventElapsedTime(&impl_->lbvhMs, impl_->ev[6], impl_->ev[7]));
     d.fnodes = ln; d.tris = lt;
   }
+  // Kernel variant for this scene shape (dev_isect.cuh TF_*).  Only a speed choice: whatever a lean variant cannot serve is deferred, ray by
+  // ray, to the generic kernels, which implement the same rules.
+  {
+    bool accelInst = false, nonFast = false, nonFastInst = false;
+    for (const FBvh& B : hs.bvhs) if (!B.fast) nonFast = true;
+    for (const FInstance& in : hs.instances) if (in.baseKind == OK_LIST || in.baseKind == OK_BVH) { accelInst = true; if (in.baseKind == OK_LIST || !hs.bvhs[in.baseIdx].fast) nonFastInst = true; }
+    if (d.accelMode == 0 || nonFastInst) impl_->shape = TF_ALL;
+    else if (accelInst || nonFast) impl_->shape = TF_LITERAL1;
+    else impl_->shape = 0;
+    if (const char* f = getenv("DRT_FORCE_SHAPE")) impl_->shape = atoi(f) & TF_ALL;      // tuning / test aid: every shape must give the same image
+    impl_->anySecondary = false; for (const FShader& sh : hs.shaders) if (sh.flags & SF_HAS_CAUSTIC) impl_->anySecondary = true;
+    if (!keepDepthHint_) impl_->depthHint = 0;
+  }
   impl_->sceneBytes = A.used;                              // bytes copied host -> device by this upload
   d.g = hs.g; d.g.pad0 = 0;
   for (const FPrim& p : hs.prims) if (p.type == PT_MOVSPHERE) d.g.pad0 = 1;
@@ -455,6 +550,11 @@ static inline unsigned gridFor(long long n, int block) { return (unsigned)((n + 
 void Renderer::renderRange(long long pix0, long long pix1, const RenderOutputs& out, RenderStats* stats) { renderChunks(pix0, pix1, 1, 0, 0, out, stats); }
 
 // world > 1: compact pixel p of this rank maps to interleaved row chunks (chunkRows rows each, chunk c of the rank = absolute chunk c*world+rank)
+//
+// One frame = batches of <= batchRays primary rays; one batch = bounce levels 0..L-1, each {closest hit, surface, [photon gather], lights}, then
+// the bottom-up resolve and the pixel pack.  Nothing on this path waits for the device: the length of every level lives in device memory
+// (Counters::levelCount), kernels of levels >= 1 run as grid-stride loops over it, and the one host sync of the call is at its end, where the
+// device error word says whether the speculation held (queue capacity, launched depth); if not, the frame is rendered again with safer settings.
 void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank, int chunkRows, const RenderOutputs& out, RenderStats* stats) {
   CK(cudaSetDevice(device_)); cudaStream_t st = (cudaStream_t)stream_; Impl& I = *impl_;
   PixMap pm; pm.totalPix = (long long)g_.cols * g_.rows; pm.world = world < 1 ? 1 : world; pm.rank = rank;
@@ -462,59 +562,91 @@ void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank,
   if (pm.world > 1) { long long nChunks = (g_.rows + chunkRows - 1) / chunkRows, mine = (nChunks - rank + world - 1) / world; pix0 = 0; pix1 = mine * pm.chunkPix; }
   if (!I.ds.prims) throw std::runtime_error("render called before a scene was uploaded");
   const unsigned long long buildLaunches0 = g_kernelLaunches;
-  devErrorReset(st);
-  if (g_.photonKind != 0 && !I.photons.built) { if (!I.photons.emitted) I.photons.emitRange(I.ds, 0, g_.numPhotonsCast, I.ctr, I.ctrHost, st); I.photons.buildGrid(I.ds, st); }
+  if (g_.photonKind != 0 && !I.photons.built) { devErrorReset(st); if (!I.photons.emitted) I.photons.emitRange(I.ds, 0, g_.numPhotonsCast, I.ctr, I.ctrHost, st); I.photons.buildGrid(I.ds, st); devErrorCheck(st); }
   const int spp = g_.spp < 1 ? 1 : g_.spp;
-  long long pixPerBatch = batchRays_ / spp; if (pixPerBatch < 1) pixPerBatch = 1;
-  RenderStats rs; std::memset(&rs, 0, sizeof(rs)); if (stats) { rs.photonSeg = stats->photonSeg; rs.photonsStored = stats->photonsStored; }
-  rs.photonsStored = I.photons.count; rs.photonSeg = I.photons.segments;
-  float msT = 0, msS = 0, msL = 0;
-  CK(cudaEventRecord(I.ev[0], st));
-  for (long long b0 = pix0; b0 < pix1; b0 += pixPerBatch) {
-    long long nPix = std::min(pixPerBatch, pix1 - b0), n0 = nPix * spp;
+  const int fullDepth = I.anySecondary ? std::max(1, std::min(g_.numRays - 1, DRT_MAX_LEVELS)) : 1;      // children spawn while gen < numRays - 2
+  const bool generic = counters_ || I.shape == TF_ALL || (traceMode_ & (256 | 512)) != 0;
+  long long batchRays = batchRays_; int levels = (I.depthHint > 0) ? std::min(fullDepth, I.depthHint + 1) : fullDepth;
+  // queue capacity of a level relative to the batch's primary rays.  2 is the true bound for level 1 and ample for every shipped scene; the true
+  // bound of level L is 2^L (binary Fresnel splits), so an overflow doubles the factor (and halves the batch: same memory) and renders again
+  double capFactor = 2.0;
+  if (const char* e = getenv("DRT_QUEUE_FACTOR")) capFactor = std::max(1e-3, atof(e));      // test aid: force the overflow path
+  if (const char* e = getenv("DRT_DEPTH_HINT")) levels = std::max(1, std::min(fullDepth, atoi(e)));    // test aid: force the depth-speculation path
+  RenderStats rs; unsigned retries = 0;
+  while (true) {
+    std::memset(&rs, 0, sizeof(rs)); rs.photonsStored = I.photons.count; rs.photonSeg = I.photons.segments;
+    long long pixPerBatch = batchRays / spp; if (pixPerBatch < 1) pixPerBatch = 1;
+    const long long maxN0 = std::min(pixPerBatch, std::max<long long>(pix1 - pix0, 1)) * spp;
+    const long long rayCap = (levels > 1) ? std::max<long long>(64, (long long)(capFactor * (double)maxN0)) : 1;
+    const long long nodeCap = (levels > 1) ? maxN0 + ((capFactor >= 64.0) ? 126 * maxN0 : std::max<long long>(64, (long long)(1.5 * capFactor * (double)maxN0))) : maxN0;
+    I.hits0.ensure(maxN0, st); I.surf.ensure(std::max(maxN0, rayCap), st); I.nodes.ensure(nodeCap, st);
+    if (levels > 1) { I.rays[0].ensure(rayCap, st); I.rays[1].ensure(rayCap, st); I.hits.ensure(rayCap, st); }
+    if (!generic) { I.deferT.ensure(std::max(maxN0, rayCap), st); I.deferL.ensure(std::max(maxN0, rayCap), st); }
+    const unsigned persist = (unsigned)std::min<long long>(gridFor(rayCap, 128), (long long)I.numSMs * 16), fixGrid = (unsigned)I.numSMs * 4;
+    devErrorReset(st);
     CK(cudaMemsetAsync(I.ctr, 0, sizeof(Counters), st));
-    std::vector<long long> lvlCount, lvlOff; long long n = n0, off = 0; int cur = 0;
-    I.rays[0].ensure(n0, st); I.nodes.ensure(n0, st, false); I.hits0.ensure(n0, st);
-    k_raygen<<<gridFor(n0, 256), 256, 0, st>>>(I.ds, pm, b0, n0, I.rays[0].p, I.nodes.p); ++rs.kernelLaunches;
-    for (int level = 0; n > 0; ++level) {
-      lvlCount.push_back(n); lvlOff.push_back(off);
-      Hit* hitBuf; if (level == 0) hitBuf = I.hits0.p; else { I.hits.ensure(n, st); hitBuf = I.hits.p; }
-      I.surf.ensure(n, st);
-      long long nextCap = 2 * n; I.rays[cur ^ 1].ensure(nextCap, st); I.nodes.ensure(off + n + nextCap, st, true);
-      CK(cudaEventRecord(I.ev[1], st));
-      if (counters_ || (traceMode_ & 512)) k_trace<true><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.rays[cur].p, hitBuf, I.ctr);
-      else k_trace<false><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.rays[cur].p, hitBuf, I.ctr);
-      CK(cudaEventRecord(I.ev[2], st));
-      k_shade<<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.rays[cur].p, hitBuf, I.surf.p, I.nodes.p + off, I.rays[cur ^ 1].p, I.nodes.p + off + n, I.ctr, nextCap);
-      if (I.ds.numPhotons > 0) { k_photon_gather_lane<<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off); k_photon_gather_warp<<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off); rs.kernelLaunches += 2; }
-      CK(cudaEventRecord(I.ev[3], st));
-      if (counters_ || (traceMode_ & 256)) k_light<true><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off, I.ctr);
-      else k_light<false><<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, I.surf.p, I.nodes.p + off, I.ctr);
-      CK(cudaEventRecord(I.ev[4], st));
-      rs.kernelLaunches += 3;
-      CK(cudaMemcpyAsync(I.ctrHost, I.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      float a, b2, c; CK(cudaEventElapsedTime(&a, I.ev[1], I.ev[2])); CK(cudaEventElapsedTime(&b2, I.ev[2], I.ev[3])); CK(cudaEventElapsedTime(&c, I.ev[3], I.ev[4]));
-      msT += a; msS += b2; msL += c;
-      long long next = (long long)I.ctrHost->nextCount; if (next > nextCap) next = nextCap;
-      CK(cudaMemsetAsync(&I.ctr->nextCount, 0, sizeof(unsigned long long), st));
-      off += n; n = next; cur ^= 1;
+    size_t evN = 0; std::vector<size_t> evIdx;      // 4 events per (batch, level): before trace, after trace, after shade (+gather), after light
+    CK(cudaEventRecord(I.pev(evN), st)); const size_t evStart = evN++;
+    for (long long b0 = pix0; b0 < pix1; b0 += pixPerBatch) {
+      const long long nPix = std::min(pixPerBatch, pix1 - b0), n0 = nPix * spp;
+      CK(cudaMemsetAsync(&I.ctr->levelCount, 0, sizeof(Counters) - offsetof(Counters, levelCount), st));
+      for (int level = 0; level < levels; ++level) {
+        Wave w; w.n0 = n0; w.rayCap = rayCap; w.nodeCap = nodeCap; w.level = level; w.launchedLevels = levels;
+        const RayRec* rays = (level == 0) ? nullptr : I.rays[level & 1].p; RayRec* nextRays = I.rays[(level + 1) & 1].p;
+        Hit* hitBuf = (level == 0) ? I.hits0.p : I.hits.p;
+        const unsigned grid = (level == 0) ? gridFor(n0, 128) : persist;
+        CK(cudaEventRecord(I.pev(evN), st)); evIdx.push_back(evN++);
+        if (generic) {
+          if (counters_ || (traceMode_ & 512)) k_trace<true, TF_ALL><<<grid, 128, 0, st>>>(I.ds, w, pm, b0, rays, hitBuf, I.ctr, nullptr, nullptr);
+          else k_trace<false, TF_ALL><<<grid, 128, 0, st>>>(I.ds, w, pm, b0, rays, hitBuf, I.ctr, nullptr, nullptr);
+          ++rs.kernelLaunches;
+        } else {
+          if (I.shape == 0) k_trace<false, 0><<<grid, 128, 0, st>>>(I.ds, w, pm, b0, rays, hitBuf, I.ctr, nullptr, I.deferT.p);
+          else k_trace<false, TF_LITERAL1><<<grid, 128, 0, st>>>(I.ds, w, pm, b0, rays, hitBuf, I.ctr, nullptr, I.deferT.p);
+          k_trace<false, TF_ALL><<<fixGrid, 128, 0, st>>>(I.ds, w, pm, b0, rays, hitBuf, I.ctr, I.deferT.p, nullptr);
+          rs.kernelLaunches += 2;
+        }
+        CK(cudaEventRecord(I.pev(evN++), st));
+        k_shade<<<grid, 128, 0, st>>>(I.ds, w, pm, b0, rays, hitBuf, I.surf.p, I.nodes.p, nextRays, I.ctr); ++rs.kernelLaunches;
+        if (I.ds.numPhotons > 0) { k_photon_gather_lane<<<grid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr); k_photon_gather_warp<<<grid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr); rs.kernelLaunches += 2; }
+        CK(cudaEventRecord(I.pev(evN++), st));
+        if (generic) {
+          if (counters_ || (traceMode_ & 256)) k_light<true, TF_ALL><<<grid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr, nullptr, nullptr);
+          else k_light<false, TF_ALL><<<grid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr, nullptr, nullptr);
+          ++rs.kernelLaunches;
+        } else {
+          if (I.shape == 0) k_light<false, 0><<<grid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr, nullptr, I.deferL.p);
+          else k_light<false, TF_LITERAL1><<<grid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr, nullptr, I.deferL.p);
+          k_light<false, TF_ALL><<<fixGrid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr, I.deferL.p, nullptr);
+          rs.kernelLaunches += 2;
+        }
+        CK(cudaEventRecord(I.pev(evN++), st));
+      }
+      for (int level = levels - 1; level >= 1; --level) {
+        Wave w; w.n0 = n0; w.rayCap = rayCap; w.nodeCap = nodeCap; w.level = level; w.launchedLevels = levels;
+        k_resolve<<<persist, 256, 0, st>>>(w, I.nodes.p, I.ctr); ++rs.kernelLaunches;
+      }
+      k_finish<<<gridFor(nPix, 256), 256, 0, st>>>(I.ds, pm, b0, nPix, I.nodes.p, I.hits0.p, out); ++rs.kernelLaunches;
     }
-    for (int level = (int)lvlCount.size() - 1; level >= 1; --level) {
-      k_resolve<<<gridFor(lvlCount[level], 256), 256, 0, st>>>(lvlCount[level], I.nodes.p + lvlOff[level], I.nodes.p + lvlOff[level - 1]); ++rs.kernelLaunches;
-    }
-    k_finish<<<gridFor(nPix, 256), 256, 0, st>>>(I.ds, pm, b0, nPix, I.nodes.p, I.hits0.p, out); ++rs.kernelLaunches;
+    CK(cudaEventRecord(I.pev(evN), st)); const size_t evEnd = evN++;
     CK(cudaMemcpyAsync(I.ctrHost, I.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    for (int k = 0; k < 64; ++k) { rs.primary += I.ctrHost->primaryS[k]; rs.shadow += I.ctrHost->shadowS[k]; }
-    rs.primary += I.ctrHost->primary; rs.shadow += I.ctrHost->shadow; rs.reflect += I.ctrHost->reflect; rs.refract += I.ctrHost->refract; rs.boxTests += I.ctrHost->box; rs.primTests += I.ctrHost->prim; rs.boxTestsClosest += I.ctrHost->boxC; rs.primTestsClosest += I.ctrHost->primC;
+    unsigned int devErr = 0; CK(cudaMemcpyFromSymbolAsync(&devErr, g_devError, sizeof(devErr), 0, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st)); CK(cudaGetLastError()); ++rs.hostSyncs;
+    if (devErr & 1u) throw std::runtime_error("traversal stack overflow on the device (acceleration structure deeper than the kernels support): the result would be incomplete");
+    if (devErr & 4u) { if (levels >= fullDepth) throw std::runtime_error("internal error: bounce depth beyond numRays"); levels = fullDepth; ++retries; continue; }
+    if (devErr & 2u) { if (capFactor >= 64.0) throw std::runtime_error("internal error: secondary-ray queues overflow at their upper bound"); capFactor = std::min(64.0, capFactor * 2); if (capFactor > 2.0) batchRays = std::max<long long>(65536, batchRays / 2); ++retries; continue; }
+    float msT = 0, msS = 0, msL = 0, tot = 0;
+    for (size_t k : evIdx) { float a, b2, c; CK(cudaEventElapsedTime(&a, I.evPool[k], I.evPool[k + 1])); CK(cudaEventElapsedTime(&b2, I.evPool[k + 1], I.evPool[k + 2])); CK(cudaEventElapsedTime(&c, I.evPool[k + 2], I.evPool[k + 3])); msT += a; msS += b2; msL += c; }
+    CK(cudaEventElapsedTime(&tot, I.evPool[evStart], I.evPool[evEnd]));
+    const Counters& C = *I.ctrHost;
+    for (int k = 0; k < 64; ++k) { rs.primary += C.primaryS[k]; rs.shadow += C.shadowS[k]; }
+    rs.primary += C.primary; rs.shadow += C.shadow; rs.reflect += C.reflect; rs.refract += C.refract; rs.boxTests += C.box; rs.primTests += C.prim; rs.boxTestsClosest += C.boxC; rs.primTestsClosest += C.primC;
+    rs.deferred = C.deferredTotal; rs.retries = retries;
+    I.depthHint = std::max(1, (int)C.maxLevel + 1);          // levels that held rays this frame: the next frame of this scene launches one more than that
+    rs.kernelLaunches += g_kernelLaunches - buildLaunches0;      // photon emission / grid build done inside this call
+    rs.msTrace = msT; rs.msShade = msS; rs.msLight = msL; rs.msTotal = tot; rs.msOther = tot - msT - msS - msL;
+    break;
   }
-  CK(cudaEventRecord(I.ev[5], st)); CK(cudaStreamSynchronize(st));
-  float tot; CK(cudaEventElapsedTime(&tot, I.ev[0], I.ev[5]));
-  CK(cudaGetLastError());
-  devErrorCheck(st);
-  rs.kernelLaunches += g_kernelLaunches - buildLaunches0;      // photon emission / grid build done inside this call
-  rs.msTrace = msT; rs.msShade = msS; rs.msLight = msL; rs.msTotal = tot; rs.msOther = tot - msT - msS - msL;
   if (stats) *stats = rs;
 }
 

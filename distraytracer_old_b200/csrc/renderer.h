@@ -10,6 +10,7 @@ struct RenderStats {
   unsigned long long boxTests, primTests, boxTestsClosest, primTestsClosest;   // only when counters are enabled
   unsigned long long photonsStored;
   unsigned long long kernelLaunches;
+  unsigned long long deferred, retries, hostSyncs;                    // rays / light records the lean kernels left to the generic pass; re-rendered frames; host syncs of the call
   double msTrace, msShade, msLight, msOther, msTotal;               // CUDA-event times of the last render call
 };
 
@@ -21,7 +22,7 @@ class Renderer {
  public:
   Renderer(int device);
   ~Renderer();
-  void upload(const HostScene& hs);                    // flat scene -> HBM
+  void upload(const HostScene& hs, bool sameScene = false);   // flat scene -> HBM (sameScene: a re-upload of what is already resident, keeps the depth hint)
   void setBatchRays(long long n) { batchRays_ = n; }
   void setCounters(bool on) { counters_ = on; }
   void setTraceMode(int m) { traceMode_ = m; }
@@ -55,6 +56,7 @@ class Renderer {
   long long batchRays_ = 8ll << 20;
   bool counters_ = false;
   int traceMode_ = 0;
+  bool keepDepthHint_ = false;
 };
 
 }  // namespace drt

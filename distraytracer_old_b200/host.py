@@ -25,7 +25,8 @@ class _Config(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays_primary", "rays_shadow", "rays_reflect", "rays_refract", "rays_photon",
                                            "box_tests", "prim_tests", "photons_stored", "kernel_launches", "box_tests_closest", "prim_tests_closest")] + \
-               [(n, C.c_double) for n in ("ms_trace", "ms_shade", "ms_light", "ms_other", "ms_total")]
+               [(n, C.c_double) for n in ("ms_trace", "ms_shade", "ms_light", "ms_other", "ms_total")] + \
+               [(n, C.c_uint64) for n in ("rays_deferred", "frame_retries", "host_syncs")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -42,6 +42,7 @@ typedef struct drt_stats {
   uint64_t box_tests, prim_tests, photons_stored, kernel_launches;
   uint64_t box_tests_closest, prim_tests_closest;                                 /* the closest-hit (k_trace) share of the two counters above */
   double ms_trace, ms_shade, ms_light, ms_other, ms_total;                      /* CUDA-event times of the call */
+  uint64_t rays_deferred, frame_retries, host_syncs;                             /* work the lean kernels handed to the generic pass; frames re-rendered after a failed speculation; host<->device syncs of the call */
 } drt_stats;
 
 /* host image decoder: PApplet.loadImage(name).pixels (myRTFileReader.java:133,265). Return 0 and fill w,h and a

@@ -65,3 +65,49 @@ def test_fast_mode_explicit_rays_from_everywhere(drt, gpu_ctx_factory):
         assert np.array_equal(res[0][0], res[1][0]), name
         assert np.array_equal(res[0][1], res[1][1]), name
         assert (res[0][0][:, 0] >= 0).sum() > 1000
+
+
+# ---- kernel variants and the sync-free wavefront loop (round 2) ------------------------------------------------------------------------
+SHAPE_SCENES = [("p3_t09", 0), ("p3_t11_sierp", 0), ("p3_t12", 0), ("p3_t05", 0), ("planets3Ortho", 4), ("plnts3ColsBunnies", 2), ("p3_t10", 0), ("c5Fish", 0), ("box_caustics", 0)]
+
+
+@pytest.mark.parametrize("name,spp", SHAPE_SCENES)
+def test_kernel_variants_give_identical_frames(drt, gpu_ctx_factory, name, spp, monkeypatch):
+    """The lean trace / light kernels (flat scenes: shape 0; instanced meshes: shape 1) defer what they cannot serve to the generic kernels
+    (shape 7).  Whatever variant the scene runs with, every buffer must be identical -- including scenes where a variant defers EVERY ray
+    (orthographic camera: axis-parallel rays; instance trees under the flat-scene kernel)."""
+    res = {}
+    for shape in (7, 0, 1):
+        monkeypatch.setenv("DRT_FORCE_SHAPE", str(shape))
+        res[shape], _ = render(drt, gpu_ctx_factory, name, drt.ACCEL_REFERENCE_FAST, 200, 150, spp)
+    monkeypatch.delenv("DRT_FORCE_SHAPE")
+    auto, _ = render(drt, gpu_ctx_factory, name, drt.ACCEL_REFERENCE_FAST, 200, 150, spp)
+    for other in (res[0], res[1], auto):
+        for k in ("argb", "hit_prim", "hit_inst", "t", "rgb"):
+            assert np.array_equal(res[7][k], other[k]), (name, k)
+        for k in ("rays_primary", "rays_shadow", "rays_reflect", "rays_refract"):
+            assert getattr(res[7]["stats"], k) == getattr(other["stats"], k)
+    assert res[7]["stats"].rays_deferred == 0
+    if name in ("planets3Ortho", "p3_t11_sierp"):
+        assert res[0]["stats"].rays_deferred > 0
+
+
+def test_frame_needs_one_host_sync_and_speculation_is_checked(drt, gpu_ctx_factory, monkeypatch):
+    """No host round trip per bounce level: level sizes live on the device.  The two speculations of the loop -- queue capacity and the number of
+    levels launched -- are verified by the device and a failed one re-renders the frame; the result never changes."""
+    ctx = gpu_ctx_factory(256, 192)
+    s = drt.Scene.from_cli(ctx, "planets3columns.cli", spp=2, accel=drt.ACCEL_REFERENCE_FAST)
+    a, st = s.draw()
+    assert st.host_syncs == 1 and st.frame_retries == 0 and st.rays_reflect + st.rays_refract > 0
+    b, st2 = s.draw()                         # second frame of the same scene: launches only the depth the first one needed (+1)
+    assert np.array_equal(a, b) and st2.frame_retries == 0 and st2.kernel_launches <= st.kernel_launches
+    monkeypatch.setenv("DRT_DEPTH_HINT", "2")
+    c, st3 = s.draw()
+    assert np.array_equal(a, c) and st3.frame_retries >= 1
+    monkeypatch.delenv("DRT_DEPTH_HINT")
+    monkeypatch.setenv("DRT_QUEUE_FACTOR", "0.05")
+    d, st4 = s.draw()
+    assert np.array_equal(a, d) and st4.frame_retries >= 1
+    for k in ("rays_primary", "rays_shadow", "rays_reflect", "rays_refract"):
+        assert getattr(st, k) == getattr(st4, k) == getattr(st3, k)
+    ctx.close()

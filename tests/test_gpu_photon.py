@@ -75,7 +75,8 @@ def test_knn_gather_matches_kdtree_and_brute_force(drt, orc, gpu_ctx_factory, na
     ctx.close()
 
 
-@pytest.mark.parametrize("name,photons,spp", [("t05", 200000, 0), ("t10", 30000, 0), ("t11", 20000, 2), ("t08", 100000, 0), ("t04", 50000, 0)])
+@pytest.mark.parametrize("name,photons,spp", [("t05", 200000, 0), ("t10", 30000, 0), ("t11", 20000, 2), ("t08", 100000, 0), ("t04", 50000, 0),
+                                              ("box_caustics", 200000, 0), ("box_gi", 30000, 0)])      # BASELINE configs[4] wrappers
 def test_photon_scene_image_matches_oracle(drt, orc, gpu_ctx_factory, name, photons, spp):
     cols = rows = 150
     ctx = gpu_ctx_factory(cols, rows)
@@ -89,6 +90,44 @@ def test_photon_scene_image_matches_oracle(drt, orc, gpu_ctx_factory, name, phot
     mse = ((ga - ra) ** 2).mean()
     assert mse == 0 or 10 * np.log10(255 ** 2 / mse) >= 40.0
     assert g["stats"].photons_stored > 0 and g["stats"].rays_photon > 0
+    ctx.close()
+
+
+def test_box_caustics_converges_to_oracle_reference(drt, orc, gpu_ctx_factory):
+    """BASELINE north star for configs[4]: the GPU render at its own photon count against a CONVERGED oracle render (8x the photons,
+    different photon paths because the counts differ): PSNR >= 40 dB.  The caustic estimate is a density estimate (k nearest within r), so
+    it converges with the photon count; 1.6 M vs 200 k cast is enough at this size."""
+    cols = rows = 160
+    ctx = gpu_ctx_factory(cols, rows)
+    g, _ = drt.Scene.from_cli(ctx, "box_caustics.cli", photons=1600000).draw()
+    r = orc.OracleScene("box_caustics.cli", cols=cols, rows=rows, photons=12800000).render(threads=os.cpu_count(), want=("argb",))
+    ga, ra = orc.argb_to_rgb8(g).astype(float), orc.argb_to_rgb8(r["argb"]).astype(float)
+    mse = ((ga - ra) ** 2).mean()
+    assert mse == 0 or 10 * np.log10(255 ** 2 / mse) >= 40.0, 10 * np.log10(255 ** 2 / mse)
+    ctx.close()
+
+
+def test_knn_gather_when_grid_cells_are_wider_than_the_radius(drt, gpu_ctx_factory, tmp_path):
+    """A tiny photon radius on a large extent makes the grid double its cell size until it fits 2^22 coarse cells: the fine sub-cells are then
+    wider than r/4, and a fine-cube search plan would look beyond the scene's radius (find_near requires d^2 < r^2, myLight.java:389-445).
+    Every query must still return the brute-force answer."""
+    (tmp_path / "wide.cli").write_text(
+        "fov 60\nbackground 0 0 0\npoint_light 0 40 -60 1 1 1\ndiffuse_photons 300000 40 0.02\ndiffuse .8 .8 .8 .1 .1 .1\n"
+        "begin\nvertex -90 -1 -150\nvertex 90 -1 -150\nvertex 90 -1 30\nend\nbegin\nvertex 90 -1 30\nvertex -90 -1 30\nvertex -90 -1 -150\nend\n"
+        "begin\nvertex -90 -1 -150\nvertex 90 -1 -150\nvertex 90 80 -150\nend\nsphere 1 0 0 -6\nwrite x.png\n")
+    ctx = gpu_ctx_factory(64, 64)
+    s = drt.Scene.from_cli(ctx, "wide.cli", data_dir=str(tmp_path))
+    ph = s.photons()
+    assert len(ph) > 10000
+    # densest spots: around the sphere (every photon that hits it lands within 1 unit) -> hundreds of photons inside one coarse cell
+    rng = np.random.default_rng(3)
+    near = ph[((ph[:, :3] - np.array([0, 0, -6.0])) ** 2).sum(axis=1) < 1.2]
+    assert len(near) > 500
+    pts = np.concatenate([near[rng.integers(0, len(near), 800), :3] + rng.normal(0, 0.004, size=(800, 3)), ph[rng.integers(0, len(ph), 300), :3]])
+    got = s.photon_probe(pts)
+    want = brute_force(ph, pts, 40, float(np.float32(0.02)) ** 2)
+    assert np.array_equal(got[:, 3], want[:, 3])
+    assert np.allclose(got[:, :3], want[:, :3], rtol=1e-12, atol=0)
     ctx.close()
 
 

@@ -86,6 +86,21 @@ def test_reference_image_t11_sierp_pin(orc):
     assert psnr_px > 21.0 and psnr_box > 31.0, (psnr_px, psnr_box)
 
 
+def test_reference_image_t11_sierp_sky_and_silhouette_pin(orc):
+    """Bit-level pin of the oracle against the reference's own render where the missing mesh cannot interfere (tests/golden/ref_masks.py):
+    every pixel the reference shows as sky (62 % of the frame) must come out within 2/255 -- measured: ALL of them identical -- which pins the
+    camera, the skydome lookup and the texel decode; the union of instance silhouettes must overlap the reference's with IoU >= 0.9
+    (measured 0.992 with the stand-in mesh), which pins the Sierpinski transform chain and the instance-level BVH."""
+    from tests.golden import ref_masks
+    ref = ref_masks.load_ref()
+    assert 0.60 < ref["sky"].mean() < 0.64
+    r = orc.OracleScene("p3_t11_sierp_d6.cli").render(threads=os.cpu_count(), want=("argb", "hit_prim"))
+    res = ref_masks.compare(ref, orc.argb_to_rgb8(r["argb"]), r["hit_prim"] >= 0)
+    assert res["sky_bad_frac"] <= 1e-3 and res["sky_exact_frac"] >= 0.999, res
+    assert res["sky_raw_bad_frac"] <= 5e-3, res          # outline band included: the stand-in's outline differs from the real bunny's by a few pixels
+    assert res["iou"] >= 0.9, res
+
+
 def test_bvh_median_split_ledger(orc, golden):
     s = orc.OracleScene("p3_t08.cli")
     d, box = s.dump_bvh(2)
