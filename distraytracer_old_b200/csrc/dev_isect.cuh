@@ -427,10 +427,12 @@ __device__ DRT_LEAN_INLINE bool fastShadow(const DScene& S, const FBvh& B, const
 // min <= max, checked by the host), so the near/far slab planes are picked per RAY, and each box costs 6 subtractions, 6 products, two
 // 3-way max/min and the margin check of boxQuick().  Anything inside the margin goes to the exact test, out of line.
 struct LeanRay { double ox, oy, oz, ix, iy, iz; bool px, py, pz; };
-__device__ __noinline__ bool boxExactLB(const double* __restrict__ box6, double ox, double oy, double oz, double ax, double ay, double az, double& te) {
-  Ray r; r.o = d3(ox, oy, oz); r.a = d3(ax, ay, az); r.d = r.a; r.norm = false; int face;
+// exact (true-division) box test, out of line; returns the entry t (> 0 by the acceptance rule) or -1 when the box is rejected.  The value
+// travels in the return register: a `double&` result would force the callers' entry-t variables into local memory on EVERY node visit.
+__device__ __noinline__ double boxExactEntry(const double* __restrict__ box6, double ox, double oy, double oz, double ax, double ay, double az) {
+  Ray r; r.o = d3(ox, oy, oz); r.a = d3(ax, ay, az); r.d = r.a; r.norm = false; int face; double te;
   double b[6]; for (int i = 0; i < 6; ++i) b[i] = __ldg(box6 + i);
-  return boxTest(b, b + 3, r, te, face);
+  return boxTest(b, b + 3, r, te, face) ? te : -1.0;
 }
 // 1 accepted / 0 rejected / -1 undecided; nearOut = entry t to ~3e-16 relative
 __device__ __forceinline__ int leanBox(double mnx, double mny, double mnz, double mxx, double mxy, double mxz, const LeanRay& R, double& nearOut) {
@@ -487,6 +489,9 @@ __device__ __forceinline__ bool leanTri(const FTri* __restrict__ T, double ox, d
   tOut = t; stOut = st; return true;
 }
 // returns 1 hit / 0 miss / -1 the CAP-entry stack overflowed (the caller defers the ray to the generic kernel or flags a device error)
+// Loop shape ("while-while"): every lane first descends inner nodes until it HOLDS A LEAF (or is finished), then the warp tests triangles
+// together -- the triangle test is the expensive, divergence-prone part (measured: 11.6 of 32 lanes active in the one-loop form).  The visiting
+// order changes nothing: the result is the minimum over all accepted leaves, ties resolved by reference rank.
 template <bool ONE_RAY, int CAP>
 __device__ DRT_LEAN_INLINE int leanClosest(const DScene& S, const FBvh& B, const D3 bo, const D3 ba, const D3 to, const D3 td, const D3 rawDir, Hit& out, TraceCounters* tc) {
   LeanRay R; R.ox = bo.x; R.oy = bo.y; R.oz = bo.z;
@@ -494,11 +499,14 @@ __device__ DRT_LEAN_INLINE int leanClosest(const DScene& S, const FBvh& B, const
   R.ix = 1.0 / ax; R.iy = 1.0 / ay; R.iz = 1.0 / az; R.px = ax > 0; R.py = ay > 0; R.pz = az > 0;
   const double tox = ONE_RAY ? R.ox : to.x, toy = ONE_RAY ? R.oy : to.y, toz = ONE_RAY ? R.oz : to.z;
   const double tdx = ONE_RAY ? ax : td.x, tdy = ONE_RAY ? ay : td.y, tdz = ONE_RAY ? az : td.z;
-  FStackT<CAP> stk; const bool stdBox = S.accelMode == 2;
+  // (stack array and its scalar state are separate variables: a struct holding a dynamically indexed array lives in local memory as a whole,
+  //  and `sp` would be re-loaded and re-stored on every push and pop)
+  uint2 stkE[CAP]; int sp = 0; bool overflow = false; const bool stdBox = S.accelMode == 2;
   double bestT = DRT_DMAX; int bestTri = -1, bestRank = 0x7fffffff, bestSt = 0;
-  int32_t ref = B.fastRoot;
+  int32_t ref = B.fastRoot; bool alive = true;
+  auto popNext = [&]() { alive = false; while (sp > 0) { const uint2 e = stkE[--sp]; if ((double)__uint_as_float(e.y) < bestT) { ref = (int32_t)e.x; alive = true; break; } } };
   while (true) {
-    if (ref >= 0) {
+    while (alive && ref >= 0) {
       const double2* q = reinterpret_cast<const double2*>(S.fnodes + ref);
       const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5);
       const int4 lk = __ldg(reinterpret_cast<const int4*>(q) + 6);
@@ -507,35 +515,32 @@ __device__ DRT_LEAN_INLINE int leanClosest(const DScene& S, const FBvh& B, const
       const int ql = stdBox ? leanBoxStd(q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, R, teL) : leanBox(q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, R, teL);
       const int qr = stdBox ? leanBoxStd(q3.x, q3.y, q4.x, q4.y, q5.x, q5.y, R, teR) : leanBox(q3.x, q3.y, q4.x, q4.y, q5.x, q5.y, R, teR);
       bool hl = ql > 0, hr = qr > 0;
-      if (ql >= 0) teL *= 0.999999999999999; else hl = boxExactLB(reinterpret_cast<const double*>(q), R.ox, R.oy, R.oz, ax, ay, az, teL);
-      if (qr >= 0) teR *= 0.999999999999999; else hr = boxExactLB(reinterpret_cast<const double*>(q) + 6, R.ox, R.oy, R.oz, ax, ay, az, teR);
+      if (ql >= 0) teL *= 0.999999999999999; else { teL = boxExactEntry(reinterpret_cast<const double*>(q), R.ox, R.oy, R.oz, ax, ay, az); hl = teL > 0; }
+      if (qr >= 0) teR *= 0.999999999999999; else { teR = boxExactEntry(reinterpret_cast<const double*>(q) + 6, R.ox, R.oy, R.oz, ax, ay, az); hr = teR > 0; }
       hl = hl && teL < bestT; hr = hr && teR < bestT;
       const int32_t cl = childRef(lk.x, lk.z), cr = childRef(lk.y, lk.w);
       if (hl && hr) {
         const bool rightFirst = teR < teL;
-        stk.push(rightFirst ? cl : cr, __double2float_rd(rightFirst ? teL : teR));
-        ref = rightFirst ? cr : cl; continue;
-      }
-      if (hl) { ref = cl; continue; }
-      if (hr) { ref = cr; continue; }
-    } else {
+        if (sp < CAP) stkE[sp++] = make_uint2((uint32_t)(rightFirst ? cl : cr), __float_as_uint(__double2float_rd(rightFirst ? teL : teR))); else overflow = true;
+        ref = rightFirst ? cr : cl;
+      } else if (hl) ref = cl;
+      else if (hr) ref = cr;
+      else popNext();
+    }
+    if (!alive) break;
+    {
       const int code = ~ref, cnt = code & 7, first = code >> 3;
       for (int i = 0; i < cnt; ++i) {
         double t; int st; int32_t rank; if (tc) ++tc->prim;
         if (leanTri(S.tris + first + i, tox, toy, toz, tdx, tdy, tdz, bestT, t, st, rank) && (t < bestT || rank < bestRank)) { bestT = t; bestTri = first + i; bestRank = rank; bestSt = st; }
       }
     }
-    while (true) {
-      if (stk.sp == 0) {
-        if (stk.overflow) return -1;
-        if (bestTri < 0) return 0;
-        out.t = bestT; out.prim = S.tris[bestTri].prim; out.arg0 = 0; out.arg1 = 0; out.state = bestSt; out.hitXform = B.triHitXform; out.shaderOverride = -1; out.inst = -1;
-        out.loc = d3((tdx * bestT) + tox, (tdy * bestT) + toy, (tdz * bestT) + toz); out.rawDir = rawDir; return 1;
-      }
-      const uint2 e = stk.pop();
-      if ((double)__uint_as_float(e.y) < bestT) { ref = (int32_t)e.x; break; }
-    }
+    popNext();
   }
+  if (overflow) return -1;
+  if (bestTri < 0) return 0;
+  out.t = bestT; out.prim = S.tris[bestTri].prim; out.arg0 = 0; out.arg1 = 0; out.state = bestSt; out.hitXform = B.triHitXform; out.shaderOverride = -1; out.inst = -1;
+  out.loc = d3((tdx * bestT) + tox, (tdy * bestT) + toy, (tdz * bestT) + toz); out.rawDir = rawDir; return 1;
 }
 template <bool ONE_RAY, int CAP>
 __device__ DRT_LEAN_INLINE int leanShadow(const DScene& S, const FBvh& B, const D3 bo, const D3 ba, const D3 to, const D3 td, double dist, TraceCounters* tc) {
@@ -544,16 +549,16 @@ __device__ DRT_LEAN_INLINE int leanShadow(const DScene& S, const FBvh& B, const 
   R.ix = 1.0 / ax; R.iy = 1.0 / ay; R.iz = 1.0 / az; R.px = ax > 0; R.py = ay > 0; R.pz = az > 0;
   const double tox = ONE_RAY ? R.ox : to.x, toy = ONE_RAY ? R.oy : to.y, toz = ONE_RAY ? R.oz : to.z;
   const double tdx = ONE_RAY ? ax : td.x, tdy = ONE_RAY ? ay : td.y, tdz = ONE_RAY ? az : td.z;
-  FStackT<CAP> stk; const bool stdBox = S.accelMode == 2;
-  int32_t ref = B.fastRoot;
+  int32_t stkE[CAP]; int sp = 0; bool overflow = false; const bool stdBox = S.accelMode == 2;
+  int32_t ref = B.fastRoot; bool alive = true, found = false;
   auto accept = [&](int q, double te, const double* box6) {       // (dist - entry) > eps, with the exact entry t only when it is too close to call
     if (q == 0) return false;
     if (stdBox) return (dist - te) > DRT_EPS;
     if (q > 0) { const double diff = dist - te, m = 1e-13 * (fabs(dist) + fabs(te)); if (diff > DRT_EPS + m) return true; if (diff < DRT_EPS - m) return false; }
-    double tx; return boxExactLB(box6, R.ox, R.oy, R.oz, ax, ay, az, tx) && (dist - tx) > DRT_EPS;
+    const double tx = boxExactEntry(box6, R.ox, R.oy, R.oz, ax, ay, az); return tx > 0 && (dist - tx) > DRT_EPS;
   };
   while (true) {
-    if (ref >= 0) {
+    while (alive && ref >= 0) {
       const double2* q = reinterpret_cast<const double2*>(S.fnodes + ref);
       const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5);
       const int4 lk = __ldg(reinterpret_cast<const int4*>(q) + 6);
@@ -563,19 +568,25 @@ __device__ DRT_LEAN_INLINE int leanShadow(const DScene& S, const FBvh& B, const 
       const int qr = stdBox ? leanBoxStd(q3.x, q3.y, q4.x, q4.y, q5.x, q5.y, R, teR) : leanBox(q3.x, q3.y, q4.x, q4.y, q5.x, q5.y, R, teR);
       const bool hl = accept(ql, teL, reinterpret_cast<const double*>(q)), hr = accept(qr, teR, reinterpret_cast<const double*>(q) + 6);
       const int32_t cl = childRef(lk.x, lk.z), cr = childRef(lk.y, lk.w);
-      if (hl && hr) { stk.push(cr, 0.f); ref = cl; continue; }
-      if (hl) { ref = cl; continue; }
-      if (hr) { ref = cr; continue; }
-    } else {
+      if (hl && hr) { if (sp < CAP) stkE[sp++] = cr; else overflow = true; ref = cl; }
+      else if (hl) ref = cl;
+      else if (hr) ref = cr;
+      else if (sp > 0) ref = stkE[--sp];
+      else alive = false;
+    }
+    if (!alive) break;
+    {
       const int code = ~ref, cnt = code & 7, first = code >> 3;
       for (int i = 0; i < cnt; ++i) {
         double t; int st; int32_t rank; if (tc) ++tc->prim;
-        if (leanTri(S.tris + first + i, tox, toy, toz, tdx, tdy, tdz, DRT_DMAX, t, st, rank) && (dist - t) > DRT_EPS) return 1;
+        if (leanTri(S.tris + first + i, tox, toy, toz, tdx, tdy, tdz, DRT_DMAX, t, st, rank) && (dist - t) > DRT_EPS) { found = true; break; }
       }
     }
-    if (stk.sp == 0) return stk.overflow ? -1 : 0;
-    ref = (int32_t)stk.pop().x;
+    if (found) break;
+    if (sp > 0) ref = stkE[--sp]; else alive = false;
   }
+  if (found) return 1;
+  return overflow ? -1 : 0;
 }
 __device__ __forceinline__ bool sameRay(const Ray& trans, const Ray& r) { return trans.o.x == r.o.x && trans.o.y == r.o.y && trans.o.z == r.o.z && trans.a.x == r.d.x && trans.a.y == r.d.y && trans.a.z == r.d.z; }
 // may this BVH be searched out of the reference's order for this pair of rays?  (through an instance the triangles see a
@@ -590,7 +601,15 @@ struct Frame { int32_t node; double tL; };     // node >= 0: "after left" of tha
 // closest hit.  Every function returns 1 (hit), 0 (miss) or -1 (this kernel variant cannot serve the ray: defer it)
 // ---------------------------------------------------------------------------------------------------------------
 template <int F, int LVL>
-__device__ int accelClosest(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc);
+__device__ __forceinline__ int accelClosestImpl(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc);
+// the generic variant keeps one outlined copy per level (code size); the lean variants inline everything so that ray / hit records stay in registers
+template <int F, int LVL>
+__device__ __noinline__ int accelClosestOut(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc) { return accelClosestImpl<F, LVL>(S, kind, idx, _ray, trans, time, out, tc); }
+template <int F, int LVL>
+__device__ __forceinline__ int accelClosest(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc) {
+  if constexpr (F == TF_ALL) return accelClosestOut<F, LVL>(S, kind, idx, _ray, trans, time, out, tc);
+  else return accelClosestImpl<F, LVL>(S, kind, idx, _ray, trans, time, out, tc);
+}
 
 // myGeomList.traverseStruct: every child gets a fresh transform of `_ray`; first strictly smaller t wins;
 // the winner's CTM becomes list.CTM x child.CTM (child.hitXform).
@@ -638,7 +657,7 @@ __device__ __forceinline__ double leafClosest(const DScene& S, int listIdx, Ray&
 // combines with "min, left wins ties", the overall winner is the DFS-first minimum over all visited leaves; the
 // per-subtree minima needed for the pruning decisions live on an explicit frame stack.
 template <int F, int LVL>
-__device__ int accelClosest(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc) {
+__device__ __forceinline__ int accelClosestImpl(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc) {
   constexpr bool LITERAL = (LVL == 1) ? ((F & TF_LITERAL1) != 0) : ((F & TF_LEVEL2) != 0);      // literal recursion compiled in at this level?
   constexpr bool NONLEAN = (LVL == 1) ? ((F & TF_NONLEAN) != 0) : ((F & TF_LEVEL2) != 0);
   const D3 inv = rayInv(trans);
@@ -761,7 +780,14 @@ __device__ __forceinline__ bool closestHit(const DScene& S, Ray& ray, double tim
 // (top-level or BVH leaf) gates on its own box with the same rule.  1 / 0 / -1 as above.
 // ---------------------------------------------------------------------------------------------------------------
 template <int F, int LVL>
-__device__ int accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc);
+__device__ __forceinline__ int accelShadowImpl(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc);
+template <int F, int LVL>
+__device__ __noinline__ int accelShadowOut(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc) { return accelShadowImpl<F, LVL>(S, kind, idx, _ray, trans, time, dist, tc); }
+template <int F, int LVL>
+__device__ __forceinline__ int accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc) {
+  if constexpr (F == TF_ALL) return accelShadowOut<F, LVL>(S, kind, idx, _ray, trans, time, dist, tc);
+  else return accelShadowImpl<F, LVL>(S, kind, idx, _ray, trans, time, dist, tc);
+}
 
 template <int F, int LVL>
 __device__ __forceinline__ int listShadow(const DScene& S, int listIdx, Ray& _ray, const Ray& trans, const D3& inv, double time, double dist, TraceCounters* tc, XfCache& xc) {
@@ -785,7 +811,7 @@ __device__ __forceinline__ int listShadow(const DScene& S, int listIdx, Ray& _ra
   return 0;
 }
 template <int F, int LVL>
-__device__ int accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc) {
+__device__ __forceinline__ int accelShadowImpl(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc) {
   constexpr bool LITERAL = (LVL == 1) ? ((F & TF_LITERAL1) != 0) : ((F & TF_LEVEL2) != 0);
   constexpr bool NONLEAN = (LVL == 1) ? ((F & TF_NONLEAN) != 0) : ((F & TF_LEVEL2) != 0);
   const D3 inv = rayInv(trans);

@@ -466,7 +466,7 @@ __device__ __forceinline__ void phApply(const DScene& S, int shIdx, const double
 }
 __global__ void __launch_bounds__(128) k_photon_gather_lane(const __grid_constant__ DScene S, Wave w, SurfRec* __restrict__ surf, NodeRec* __restrict__ nodesBase, const Counters* ctr) {
   __shared__ PhLaneShared sm;
-  const long long n = waveCount(w, ctr); NodeRec* __restrict__ nodes = nodesBase + ((w.level == 0) ? 0 : waveNodeOffset(ctr, w.level));
+  const long long n = waveCount(w, ctr); NodeRec* __restrict__ nodes = nodesBase + ((w.level == 0) ? 0 : waveNodeOffset(w, ctr, w.level));
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const SurfRec s = surf[i]; if (!s.valid) continue;
     const FShader& sh = S.shaders[s.shader];
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(128) k_photon_gather_lane(const __grid_constan
 }
 __global__ void __launch_bounds__(128) k_photon_gather_warp(const __grid_constant__ DScene S, Wave w, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodesBase, const Counters* ctr) {
   __shared__ PhWarpTierShared sm;
-  const long long n = waveCount(w, ctr); NodeRec* __restrict__ nodes = nodesBase + ((w.level == 0) ? 0 : waveNodeOffset(ctr, w.level));
+  const long long n = waveCount(w, ctr); NodeRec* __restrict__ nodes = nodesBase + ((w.level == 0) ? 0 : waveNodeOffset(w, ctr, w.level));
   for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
     const long long i = base + threadIdx.x;
     bool pending = false; D3 loc = d3(0, 0, 0); int shIdx = -1;

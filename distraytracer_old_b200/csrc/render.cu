@@ -47,27 +47,38 @@ struct Counters {
 // wavefront geometry of one launch: level 0 holds n0 primary rays generated on the fly (no ray records), level L >= 1 holds levelCount[L]
 // rays that level L-1's surface pass enqueued.  Node records of all levels of a batch are contiguous: level L starts at sum(levelCount[0..L-1]).
 struct Wave { long long n0, rayCap, nodeCap; int level, launchedLevels; };
+// (an overflowing level -- flagged, the frame is rendered again -- still has its counter bumped by every warp: clamp what is processed to what
+// was actually stored, min(queue capacity, rest of the node pool), cumulatively over the levels below)
+__device__ __forceinline__ long long waveNodeOffset(const Wave& w, const Counters* ctr, int level) {
+  long long off = 0;
+  for (int l = 0; l < level; ++l) { long long c = (long long)ctr->levelCount[l]; if (l > 0) { if (c > w.rayCap) c = w.rayCap; if (c > w.nodeCap - off) c = w.nodeCap - off; } off += c; }
+  return off;
+}
 __device__ __forceinline__ long long waveCount(const Wave& w, const Counters* ctr) {
   if (w.level == 0) return w.n0;
-  const long long c = (long long)ctr->levelCount[w.level]; return c < w.rayCap ? c : w.rayCap;
-}
-__device__ __forceinline__ long long waveNodeOffset(const Counters* ctr, int level) {
-  long long off = 0; for (int l = 0; l < level; ++l) off += (long long)ctr->levelCount[l]; return off;
+  long long c = (long long)ctr->levelCount[w.level]; const long long room = w.nodeCap - waveNodeOffset(w, ctr, w.level);
+  if (c > w.rayCap) c = w.rayCap; if (c > room) c = room; return c;
 }
 
-// 16-byte-granular streaming (evict-first) copies of the 16-byte-aligned wavefront records
-template <class T> __device__ __forceinline__ void streamLoad(T* dst, const T* src) {
-  static_assert(sizeof(T) % 16 == 0, "record size");
-  int4* d = reinterpret_cast<int4*>(dst); const int4* q = reinterpret_cast<const int4*>(src);
-#pragma unroll
-  for (int k = 0; k < (int)(sizeof(T) / 16); ++k) d[k] = __ldcs(q + k);
+// Streaming (evict-first) access to the 16-byte-aligned wavefront records, field by field through registers: taking the address of a record
+// variable (a generic memcpy) would pin the whole record in local memory for the lifetime of the kernel.
+__device__ __forceinline__ int4 packDD(double a, double b) { return make_int4(__double2loint(a), __double2hiint(a), __double2loint(b), __double2hiint(b)); }
+__device__ __forceinline__ double lo64(const int4& v) { return __hiloint2double(v.y, v.x); }
+__device__ __forceinline__ double hi64(const int4& v) { return __hiloint2double(v.w, v.z); }
+__device__ __forceinline__ void loadRayRec(RayRec& r, const RayRec* __restrict__ src) {
+  const int4* q = reinterpret_cast<const int4*>(src);
+  const int4 a = __ldcs(q), b = __ldcs(q + 1), c = __ldcs(q + 2), d = __ldcs(q + 3), e = __ldcs(q + 4), f = __ldcs(q + 5);
+  r.o[0] = lo64(a); r.o[1] = hi64(a); r.o[2] = lo64(b); r.d[0] = hi64(b); r.d[1] = lo64(c); r.d[2] = hi64(c); r.kt0 = lo64(d); r.kt1 = hi64(d);
+  r.ka = (uint32_t)e.x; r.kb = (uint32_t)e.y; r.kc = (uint32_t)e.z; r.stream = (uint32_t)e.w; r.gen = f.x; r.valid = f.y; r.pad[0] = f.z; r.pad[1] = f.w;
 }
-template <class T> __device__ __forceinline__ void streamStore(T* dst, const T* src) {
-  static_assert(sizeof(T) % 16 == 0, "record size");
-  int4* d = reinterpret_cast<int4*>(dst); const int4* q = reinterpret_cast<const int4*>(src);
-#pragma unroll
-  for (int k = 0; k < (int)(sizeof(T) / 16); ++k) __stcs(d + k, q[k]);
+__device__ __forceinline__ void storeHit(Hit* __restrict__ dst, const Hit& h) {
+  int4* d = reinterpret_cast<int4*>(dst);
+  __stcs(d, make_int4(__double2loint(h.t), __double2hiint(h.t), h.prim, h.arg0));
+  __stcs(d + 1, make_int4(h.arg1, h.state, h.hitXform, h.shaderOverride));
+  __stcs(d + 2, make_int4(h.inst, h.pad0, __double2loint(h.loc.x), __double2hiint(h.loc.x)));
+  __stcs(d + 3, packDD(h.loc.y, h.loc.z)); __stcs(d + 4, packDD(h.rawDir.x, h.rawDir.y)); __stcs(d + 5, packDD(h.rawDir.z, h.pad1));
 }
+static_assert(sizeof(RayRec) == 96 && sizeof(Hit) == 96, "record layout");
 __device__ __forceinline__ void warpAdd(unsigned long long* dst, unsigned long long v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
@@ -154,14 +165,14 @@ k_trace(const __grid_constant__ DScene S, Wave w, PixMap pm, long long pix0, con
       if (work) i = work[i];
       // the ray / hit records are pure streams (read once, written once): evict-first loads and stores keep them from pushing the scene and the
       // local-memory traversal state out of L2
-      RayRec r; if (rays) streamLoad(&r, rays + i); else primaryRay(S, pm, pix0, i, r);
+      RayRec r; if (rays) loadRayRec(r, rays + i); else primaryRay(S, pm, pix0, i, r);
       Hit h; hitReset(h);
       if (r.valid) {
         Ray ray = makeRay(d3(r.o[0], r.o[1], r.o[2]), d3(r.d[0], r.d[1], r.d[2]));
         const int got = closestHitT<F>(S, ray, rayTime(S, r.stream, r.ka, r.kb, r.kc, r.stream == STREAM_PIXEL ? DIM_TIME : 0xFFFFu), h, COUNT ? &tc : nullptr);
         if (F != TF_ALL && got < 0) { defer = true; hitReset(h); }
       }
-      if (!defer) streamStore(hits + i, &h);
+      if (!defer) storeHit(hits + i, h);
     }
     if (F != TF_ALL) deferAppend(defer, (uint32_t)i, &ctr->deferTrace[w.level], deferOut);
   }
@@ -198,7 +209,7 @@ __device__ inline D3 skyColor(const DScene& S, D3 o, D3 d) {
 __global__ void __launch_bounds__(128, DRT_SHADE_MINBLOCKS) k_shade(const __grid_constant__ DScene S, Wave w, PixMap pm, long long pix0, const RayRec* __restrict__ rays, const Hit* __restrict__ hits,
                                                SurfRec* __restrict__ surf, NodeRec* __restrict__ nodesBase, RayRec* __restrict__ nextRays, Counters* ctr) {
   const long long n = waveCount(w, ctr);
-  const long long off = (w.level == 0) ? 0 : waveNodeOffset(ctr, w.level), offNext = off + ((w.level == 0) ? w.n0 : (long long)ctr->levelCount[w.level]);
+  const long long off = (w.level == 0) ? 0 : waveNodeOffset(w, ctr, w.level), offNext = off + n;
   NodeRec* __restrict__ nodes = nodesBase + off; NodeRec* __restrict__ nextNodes = nodesBase + offNext;
   const long long nextCap = (w.nodeCap - offNext) < w.rayCap ? (w.nodeCap - offNext) : w.rayCap;
   const unsigned lane = threadIdx.x & 31;
@@ -296,7 +307,7 @@ template <bool COUNT, int F>
 __global__ void __launch_bounds__(128, (F == TF_ALL) ? DRT_LIGHT_MINBLOCKS : DRT_LLIGHT_MINBLOCKS)
 k_light(const __grid_constant__ DScene S, Wave w, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodesBase, Counters* ctr, const uint32_t* __restrict__ work, uint32_t* __restrict__ deferOut) {
   const long long n = work ? (long long)ctr->deferLight[w.level] : waveCount(w, ctr);
-  NodeRec* __restrict__ nodes = nodesBase + ((w.level == 0) ? 0 : waveNodeOffset(ctr, w.level));
+  NodeRec* __restrict__ nodes = nodesBase + ((w.level == 0) ? 0 : waveNodeOffset(w, ctr, w.level));
   if (work && n > 0 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr->deferredTotal, (unsigned long long)n);
   TraceCounters tc; tc.box = 0; tc.prim = 0; unsigned long long cShadow = 0;
   for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
@@ -353,7 +364,7 @@ __device__ __forceinline__ D3 nodeTotal(const NodeRec& nd) {
 }
 // level L -> level L-1: parent.slot = w (.) clamp1(total(child)).  The level's length and position are read from the device counters.
 __global__ void k_resolve(Wave w, NodeRec* __restrict__ nodesBase, const Counters* ctr) {
-  const long long n = waveCount(w, ctr), off = waveNodeOffset(ctr, w.level), offP = off - (long long)ctr->levelCount[w.level - 1];
+  const long long n = waveCount(w, ctr), off = waveNodeOffset(w, ctr, w.level), offP = waveNodeOffset(w, ctr, w.level - 1);
   const NodeRec* __restrict__ lvl = nodesBase + off; NodeRec* __restrict__ parentLvl = nodesBase + offP;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const NodeRec nd = lvl[i]; D3 c = nodeTotal(nd);
@@ -445,6 +456,7 @@ struct Renderer::Impl {
   int shape = TF_ALL;                            // kernel variant the uploaded scene runs with (see chooseShape)
   bool anySecondary = false;                     // some shader can spawn reflection / refraction rays
   int depthHint = 0;                             // levels the last frame of this scene needed (0 = unknown: launch the full depth)
+  double capHint = 0;                            // queue-capacity factor the last frame of this scene ended up with (0 = default)
   int numSMs = 148;
   cudaEvent_t pev(size_t k) { while (evPool.size() <= k) { cudaEvent_t e; CK(cudaEventCreate(&e)); evPool.push_back(e); } return evPool[k]; }
   DBuf<int32_t> oArgb, oPrim, oInst; DBuf<double> oRgb, oT;
@@ -534,7 +546,7 @@ void Renderer::upload(const HostScene& hs, bool sameScene) {
     else impl_->shape = 0;
     if (const char* f = getenv("DRT_FORCE_SHAPE")) impl_->shape = atoi(f) & TF_ALL;      // tuning / test aid: every shape must give the same image
     impl_->anySecondary = false; for (const FShader& sh : hs.shaders) if (sh.flags & SF_HAS_CAUSTIC) impl_->anySecondary = true;
-    if (!keepDepthHint_) impl_->depthHint = 0;
+    if (!keepDepthHint_) { impl_->depthHint = 0; impl_->capHint = 0; }
   }
   impl_->sceneBytes = A.used;                              // bytes copied host -> device by this upload
   d.g = hs.g; d.g.pad0 = 0;
@@ -569,7 +581,7 @@ void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank,
   long long batchRays = batchRays_; int levels = (I.depthHint > 0) ? std::min(fullDepth, I.depthHint + 1) : fullDepth;
   // queue capacity of a level relative to the batch's primary rays.  2 is the true bound for level 1 and ample for every shipped scene; the true
   // bound of level L is 2^L (binary Fresnel splits), so an overflow doubles the factor (and halves the batch: same memory) and renders again
-  double capFactor = 2.0;
+  double capFactor = std::max(2.0, I.capHint);
   if (const char* e = getenv("DRT_QUEUE_FACTOR")) capFactor = std::max(1e-3, atof(e));      // test aid: force the overflow path
   if (const char* e = getenv("DRT_DEPTH_HINT")) levels = std::max(1, std::min(fullDepth, atoi(e)));    // test aid: force the depth-speculation path
   RenderStats rs; unsigned retries = 0;
@@ -578,13 +590,16 @@ void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank,
     long long pixPerBatch = batchRays / spp; if (pixPerBatch < 1) pixPerBatch = 1;
     const long long maxN0 = std::min(pixPerBatch, std::max<long long>(pix1 - pix0, 1)) * spp;
     const long long rayCap = (levels > 1) ? std::max<long long>(64, (long long)(capFactor * (double)maxN0)) : 1;
-    const long long nodeCap = (levels > 1) ? maxN0 + ((capFactor >= 64.0) ? 126 * maxN0 : std::max<long long>(64, (long long)(1.5 * capFactor * (double)maxN0))) : maxN0;
+    const long long nodeCap = (levels > 1) ? maxN0 + ((capFactor >= 64.0) ? 126 * maxN0 : std::max<long long>(64, (long long)(3.0 * capFactor * (double)maxN0))) : maxN0;
     I.hits0.ensure(maxN0, st); I.surf.ensure(std::max(maxN0, rayCap), st); I.nodes.ensure(nodeCap, st);
     if (levels > 1) { I.rays[0].ensure(rayCap, st); I.rays[1].ensure(rayCap, st); I.hits.ensure(rayCap, st); }
     if (!generic) { I.deferT.ensure(std::max(maxN0, rayCap), st); I.deferL.ensure(std::max(maxN0, rayCap), st); }
     const unsigned persist = (unsigned)std::min<long long>(gridFor(rayCap, 128), (long long)I.numSMs * 16), fixGrid = (unsigned)I.numSMs * 4;
     devErrorReset(st);
     CK(cudaMemsetAsync(I.ctr, 0, sizeof(Counters), st));
+    static const bool syncDebug = getenv("DRT_SYNC_DEBUG") != nullptr;      // debugging aid: locate a faulting kernel
+    auto dbg = [&](const char* what, int level) { if (!syncDebug) return; cudaError_t e = cudaStreamSynchronize(st); if (e == cudaSuccess) e = cudaGetLastError();
+      if (e != cudaSuccess) throw std::runtime_error(std::string("DRT_SYNC_DEBUG: ") + what + " level " + std::to_string(level) + ": " + cudaGetErrorString(e)); };
     size_t evN = 0; std::vector<size_t> evIdx;      // 4 events per (batch, level): before trace, after trace, after shade (+gather), after light
     CK(cudaEventRecord(I.pev(evN), st)); const size_t evStart = evN++;
     for (long long b0 = pix0; b0 < pix1; b0 += pixPerBatch) {
@@ -599,34 +614,36 @@ void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank,
         if (generic) {
           if (counters_ || (traceMode_ & 512)) k_trace<true, TF_ALL><<<grid, 128, 0, st>>>(I.ds, w, pm, b0, rays, hitBuf, I.ctr, nullptr, nullptr);
           else k_trace<false, TF_ALL><<<grid, 128, 0, st>>>(I.ds, w, pm, b0, rays, hitBuf, I.ctr, nullptr, nullptr);
-          ++rs.kernelLaunches;
+          ++rs.kernelLaunches; dbg("k_trace generic", level);
         } else {
           if (I.shape == 0) k_trace<false, 0><<<grid, 128, 0, st>>>(I.ds, w, pm, b0, rays, hitBuf, I.ctr, nullptr, I.deferT.p);
           else k_trace<false, TF_LITERAL1><<<grid, 128, 0, st>>>(I.ds, w, pm, b0, rays, hitBuf, I.ctr, nullptr, I.deferT.p);
+          dbg("k_trace lean", level);
           k_trace<false, TF_ALL><<<fixGrid, 128, 0, st>>>(I.ds, w, pm, b0, rays, hitBuf, I.ctr, I.deferT.p, nullptr);
-          rs.kernelLaunches += 2;
+          rs.kernelLaunches += 2; dbg("k_trace fix-up", level);
         }
         CK(cudaEventRecord(I.pev(evN++), st));
-        k_shade<<<grid, 128, 0, st>>>(I.ds, w, pm, b0, rays, hitBuf, I.surf.p, I.nodes.p, nextRays, I.ctr); ++rs.kernelLaunches;
-        if (I.ds.numPhotons > 0) { k_photon_gather_lane<<<grid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr); k_photon_gather_warp<<<grid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr); rs.kernelLaunches += 2; }
+        k_shade<<<grid, 128, 0, st>>>(I.ds, w, pm, b0, rays, hitBuf, I.surf.p, I.nodes.p, nextRays, I.ctr); ++rs.kernelLaunches; dbg("k_shade", level);
+        if (I.ds.numPhotons > 0) { k_photon_gather_lane<<<grid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr); k_photon_gather_warp<<<grid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr); rs.kernelLaunches += 2; dbg("k_photon_gather", level); }
         CK(cudaEventRecord(I.pev(evN++), st));
         if (generic) {
           if (counters_ || (traceMode_ & 256)) k_light<true, TF_ALL><<<grid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr, nullptr, nullptr);
           else k_light<false, TF_ALL><<<grid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr, nullptr, nullptr);
-          ++rs.kernelLaunches;
+          ++rs.kernelLaunches; dbg("k_light generic", level);
         } else {
           if (I.shape == 0) k_light<false, 0><<<grid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr, nullptr, I.deferL.p);
           else k_light<false, TF_LITERAL1><<<grid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr, nullptr, I.deferL.p);
+          dbg("k_light lean", level);
           k_light<false, TF_ALL><<<fixGrid, 128, 0, st>>>(I.ds, w, I.surf.p, I.nodes.p, I.ctr, I.deferL.p, nullptr);
-          rs.kernelLaunches += 2;
+          rs.kernelLaunches += 2; dbg("k_light fix-up", level);
         }
         CK(cudaEventRecord(I.pev(evN++), st));
       }
       for (int level = levels - 1; level >= 1; --level) {
         Wave w; w.n0 = n0; w.rayCap = rayCap; w.nodeCap = nodeCap; w.level = level; w.launchedLevels = levels;
-        k_resolve<<<persist, 256, 0, st>>>(w, I.nodes.p, I.ctr); ++rs.kernelLaunches;
+        k_resolve<<<persist, 256, 0, st>>>(w, I.nodes.p, I.ctr); ++rs.kernelLaunches; dbg("k_resolve", level);
       }
-      k_finish<<<gridFor(nPix, 256), 256, 0, st>>>(I.ds, pm, b0, nPix, I.nodes.p, I.hits0.p, out); ++rs.kernelLaunches;
+      k_finish<<<gridFor(nPix, 256), 256, 0, st>>>(I.ds, pm, b0, nPix, I.nodes.p, I.hits0.p, out); ++rs.kernelLaunches; dbg("k_finish", 0);
     }
     CK(cudaEventRecord(I.pev(evN), st)); const size_t evEnd = evN++;
     CK(cudaMemcpyAsync(I.ctrHost, I.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
@@ -642,6 +659,7 @@ void Renderer::renderChunks(long long pix0, long long pix1, int world, int rank,
     for (int k = 0; k < 64; ++k) { rs.primary += C.primaryS[k]; rs.shadow += C.shadowS[k]; }
     rs.primary += C.primary; rs.shadow += C.shadow; rs.reflect += C.reflect; rs.refract += C.refract; rs.boxTests += C.box; rs.primTests += C.prim; rs.boxTestsClosest += C.boxC; rs.primTestsClosest += C.primC;
     rs.deferred = C.deferredTotal; rs.retries = retries;
+    I.capHint = capFactor;
     I.depthHint = std::max(1, (int)C.maxLevel + 1);          // levels that held rays this frame: the next frame of this scene launches one more than that
     rs.kernelLaunches += g_kernelLaunches - buildLaunches0;      // photon emission / grid build done inside this call
     rs.msTrace = msT; rs.msShade = msS; rs.msLight = msL; rs.msTotal = tot; rs.msOther = tot - msT - msS - msL;
