@@ -334,6 +334,9 @@ enum : int { TF_LITERAL1 = 1,     // literal (reference-order) BVH recursion at 
              TF_LEVEL2 = 2,       // literal recursion / non-lean descent inside instanced accels
              TF_NONLEAN = 4,      // near-first descent with the generic slab test (irregular directions) at the top level
              TF_ALL = 7 };
+#ifndef DRT_LEAN32
+#define DRT_LEAN32 1             // lean kernels take box decisions in FP32 under an error bound (leanClosest32); 0 = FP64 lean descent everywhere
+#endif
 #ifndef DRT_LSTACK
 #define DRT_LSTACK 32            // short traversal stack of the lean kernels (a <=5-per-leaf median tree over 2^24 triangles is 23 deep)
 #endif
@@ -588,6 +591,137 @@ __device__ DRT_LEAN_INLINE int leanShadow(const DScene& S, const FBvh& B, const 
   if (found) return 1;
   return overflow ? -1 : 0;
 }
+// ---------------------------------------------------------------------------------------------------------------
+// FP32 pre-test descent of the lean kernels.
+// A node visit of the FP64 descent above costs ~160 instructions, 46 of them on the half-rate FP64 pipe.  Almost every box decision is far
+// from its boundary, so it is taken in FP32 on a 64-byte mirror of the node (FNode32: 4 loads instead of 7) under a rigorous error bound, and
+// only an undecidable box goes to the reference's own FP64 test (true divisions, out of line).  Bound: with u = 2^-24, b32 = fl(b),
+// inv32 = fl(1/a), oi32 = fl(o/a) and t32 = fma(b32, inv32, -oi32) (one rounding),
+//     |t32 - (b - o)/a| <= u (3 |b/a| + 2 |o/a|) (1 + O(u)),        |b| <= absMax (per BVH, per axis),
+// and the reference's FP64 quotient is within 2.3e-16 (|b/a| + |o/a|) of the same real number.  M = 1.1 u max_axis (3 absMax + 2 |o|) |1/a|
+// (+ a denormal floor) therefore bounds the error of every slab value of the ray; min / max are 1-Lipschitz, so near32 / far32 are within M of
+// the reference's biggestMin / min(tMax).  A box is ACCEPTED when far32 - near32 > 2M and near32 > M (=> far > near and near > 0 in the
+// reference's arithmetic), REJECTED when far32 - near32 < -2M or near32 < -M, otherwise undecided.  Rays whose reciprocals or products leave the
+// comfortable float range get M = +inf: every comparison fails and every box takes the exact test.  Entry times only order and prune
+// (conservative lower bound near32 - M), exactly as in the FP64 descent; triangles are always tested in FP64.
+struct Lean32 { float ix, iy, iz, ox, oy, oz, M, M2; };
+__device__ __forceinline__ Lean32 makeLean32(const FBvh& B, double ox, double oy, double oz, double ax, double ay, double az) {
+  const double ix = 1.0 / ax, iy = 1.0 / ay, iz = 1.0 / az; Lean32 L;
+  L.ix = (float)ix; L.iy = (float)iy; L.iz = (float)iz; L.ox = (float)(ox * ix); L.oy = (float)(oy * iy); L.oz = (float)(oz * iz);
+  const double ex = (3.0 * B.absMax[0] + 2.0 * fabs(ox)) * fabs(ix), ey = (3.0 * B.absMax[1] + 2.0 * fabs(oy)) * fabs(iy), ez = (3.0 * B.absMax[2] + 2.0 * fabs(oz)) * fabs(iz);
+  double m = ex > ey ? ex : ey; m = ez > m ? ez : m;
+  const double lim = 1e15; const bool sane = fabs(ix) < lim && fabs(iy) < lim && fabs(iz) < lim && fabs(ix) > 1e-15 && fabs(iy) > 1e-15 && fabs(iz) > 1e-15 &&
+                                             B.absMax[0] < lim && B.absMax[1] < lim && B.absMax[2] < lim && m < 1e30;
+  L.M = sane ? __double2float_ru(m * (1.1 * 5.9604644775390625e-8) + 1e-30) : __int_as_float(0x7f800000);
+  L.M2 = 2.0f * L.M; return L;
+}
+// 1 accepted / 0 rejected / -1 undecided; nearOut = near32 (within M of the reference's entry t)
+__device__ __forceinline__ int leanBox32(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const Lean32& L, bool stdBox, float& nearOut) {
+  const float t1x = __fmaf_rn(mnx, L.ix, -L.ox), t2x = __fmaf_rn(mxx, L.ix, -L.ox), t1y = __fmaf_rn(mny, L.iy, -L.oy), t2y = __fmaf_rn(mxy, L.iy, -L.oy), t1z = __fmaf_rn(mnz, L.iz, -L.oz), t2z = __fmaf_rn(mxz, L.iz, -L.oz);
+  float near_ = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
+  const float far_ = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
+  if (stdBox) { near_ = fmaxf(near_, 0.0f); nearOut = near_; const float gap = far_ - near_; return gap > L.M2 ? 1 : (gap < -L.M2 ? 0 : -1); }      // conventional: far >= max(near, 0)
+  nearOut = near_; const float gap = far_ - near_;
+  if (gap > L.M2 && near_ > L.M) return 1;
+  if (gap < -L.M2 || near_ < -L.M) return 0;
+  return -1;
+}
+// conventional slab test (LBVH mode) out of line, the arithmetic of leanBoxStd(): entry t (>= 0) or -1
+__device__ __noinline__ double boxStdEntry(const double* __restrict__ box6, double ox, double oy, double oz, double ax, double ay, double az) {
+  LeanRay R; R.ox = ox; R.oy = oy; R.oz = oz; R.ix = 1.0 / ax; R.iy = 1.0 / ay; R.iz = 1.0 / az; R.px = ax > 0; R.py = ay > 0; R.pz = az > 0;
+  double te; return leanBoxStd(__ldg(box6), __ldg(box6 + 1), __ldg(box6 + 2), __ldg(box6 + 3), __ldg(box6 + 4), __ldg(box6 + 5), R, te) > 0 ? te : -1.0;
+}
+template <int CAP>
+__device__ DRT_LEAN_INLINE int leanClosest32(const DScene& S, const FBvh& B, const D3 bo, const D3 ba, const D3 to, const D3 td, const D3 rawDir, Hit& out) {
+  const Lean32 L = makeLean32(B, bo.x, bo.y, bo.z, ba.x, ba.y, ba.z);
+  const bool stdBox = S.accelMode == 2;
+  uint2 stkE[CAP]; int sp = 0; bool overflow = false;
+  double bestT = DRT_DMAX; float bestTf = __int_as_float(0x7f800000);        // bestTf = bestT rounded UP: te_lb >= bestTf implies te >= bestT
+  int bestTri = -1, bestRank = 0x7fffffff, bestSt = 0;
+  int32_t ref = B.fastRoot; bool alive = true;
+  auto popNext = [&]() { alive = false; while (sp > 0) { const uint2 e = stkE[--sp]; if (__uint_as_float(e.y) < bestTf) { ref = (int32_t)e.x; alive = true; break; } } };
+  auto exact = [&](const FNode* nd, int side) -> float {     // undecided box: the reference's own test; returns a lower bound of the entry t, or -1 (rejected)
+    const double* b6 = reinterpret_cast<const double*>(nd) + 6 * side;
+    const double te = stdBox ? boxStdEntry(b6, bo.x, bo.y, bo.z, ba.x, ba.y, ba.z) : boxExactEntry(b6, bo.x, bo.y, bo.z, ba.x, ba.y, ba.z);
+    return (stdBox ? te >= 0 : te > 0) ? __double2float_rd(te) : -1.0f;
+  };
+  while (true) {
+    while (alive && ref >= 0) {
+      const float4* q = reinterpret_cast<const float4*>(S.fnodes32 + ref);
+      const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2); const int4 lk = __ldg(reinterpret_cast<const int4*>(q) + 3);
+      float teL, teR;
+      const int ql = leanBox32(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, L, stdBox, teL), qr = leanBox32(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, L, stdBox, teR);
+      bool hl = ql > 0, hr = qr > 0;
+      if (ql >= 0) teL -= L.M; else { teL = exact(S.fnodes + ref, 0); hl = teL >= 0; }
+      if (qr >= 0) teR -= L.M; else { teR = exact(S.fnodes + ref, 1); hr = teR >= 0; }
+      hl = hl && teL < bestTf; hr = hr && teR < bestTf;
+      const int32_t cl = childRef(lk.x, lk.z), cr = childRef(lk.y, lk.w);
+      if (hl && hr) {
+        const bool rightFirst = teR < teL;
+        if (sp < CAP) stkE[sp++] = make_uint2((uint32_t)(rightFirst ? cl : cr), __float_as_uint(rightFirst ? teL : teR)); else overflow = true;
+        ref = rightFirst ? cr : cl;
+      } else if (hl) ref = cl;
+      else if (hr) ref = cr;
+      else popNext();
+    }
+    if (!alive) break;
+    {
+      const int code = ~ref, cnt = code & 7, first = code >> 3;
+      for (int i = 0; i < cnt; ++i) {
+        double t; int st; int32_t rank;
+        if (leanTri(S.tris + first + i, to.x, to.y, to.z, td.x, td.y, td.z, bestT, t, st, rank) && (t < bestT || rank < bestRank)) { bestT = t; bestTf = __double2float_ru(t); bestTri = first + i; bestRank = rank; bestSt = st; }
+      }
+    }
+    popNext();
+  }
+  if (overflow) return -1;
+  if (bestTri < 0) return 0;
+  out.t = bestT; out.prim = S.tris[bestTri].prim; out.arg0 = 0; out.arg1 = 0; out.state = bestSt; out.hitXform = B.triHitXform; out.shaderOverride = -1; out.inst = -1;
+  out.loc = d3((td.x * bestT) + to.x, (td.y * bestT) + to.y, (td.z * bestT) + to.z); out.rawDir = rawDir; return 1;
+}
+template <int CAP>
+__device__ DRT_LEAN_INLINE int leanShadow32(const DScene& S, const FBvh& B, const D3 bo, const D3 ba, const D3 to, const D3 td, double dist) {
+  const Lean32 L = makeLean32(B, bo.x, bo.y, bo.z, ba.x, ba.y, ba.z);
+  const bool stdBox = S.accelMode == 2;
+  // (dist - entry) > eps decided on near32 when it clears the bound: entry < dist - eps - M  /  entry > dist - eps + M
+  const float accBelow = __double2float_rd((dist - DRT_EPS) - (double)L.M * 1.000001), rejAbove = __double2float_ru((dist - DRT_EPS) + (double)L.M * 1.000001);
+  int32_t stkE[CAP]; int sp = 0; bool overflow = false;
+  int32_t ref = B.fastRoot; bool alive = true, found = false;
+  auto accept = [&](int q, float te, const FNode* nd, int side) {
+    if (q == 0) return false;
+    if (q > 0) { if (te < accBelow) return true; if (te > rejAbove) return false; }
+    const double* b6 = reinterpret_cast<const double*>(nd) + 6 * side;
+    const double tx = stdBox ? boxStdEntry(b6, bo.x, bo.y, bo.z, ba.x, ba.y, ba.z) : boxExactEntry(b6, bo.x, bo.y, bo.z, ba.x, ba.y, ba.z);
+    return (stdBox ? tx >= 0 : tx > 0) && (dist - tx) > DRT_EPS;
+  };
+  while (true) {
+    while (alive && ref >= 0) {
+      const float4* q = reinterpret_cast<const float4*>(S.fnodes32 + ref);
+      const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2); const int4 lk = __ldg(reinterpret_cast<const int4*>(q) + 3);
+      float teL, teR;
+      const int ql = leanBox32(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, L, stdBox, teL), qr = leanBox32(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, L, stdBox, teR);
+      const bool hl = accept(ql, teL, S.fnodes + ref, 0), hr = accept(qr, teR, S.fnodes + ref, 1);
+      const int32_t cl = childRef(lk.x, lk.z), cr = childRef(lk.y, lk.w);
+      if (hl && hr) { if (sp < CAP) stkE[sp++] = cr; else overflow = true; ref = cl; }
+      else if (hl) ref = cl;
+      else if (hr) ref = cr;
+      else if (sp > 0) ref = stkE[--sp];
+      else alive = false;
+    }
+    if (!alive) break;
+    {
+      const int code = ~ref, cnt = code & 7, first = code >> 3;
+      for (int i = 0; i < cnt; ++i) {
+        double t; int st; int32_t rank;
+        if (leanTri(S.tris + first + i, to.x, to.y, to.z, td.x, td.y, td.z, DRT_DMAX, t, st, rank) && (dist - t) > DRT_EPS) { found = true; break; }
+      }
+    }
+    if (found) break;
+    if (sp > 0) ref = stkE[--sp]; else alive = false;
+  }
+  if (found) return 1;
+  return overflow ? -1 : 0;
+}
 __device__ __forceinline__ bool sameRay(const Ray& trans, const Ray& r) { return trans.o.x == r.o.x && trans.o.y == r.o.y && trans.o.z == r.o.z && trans.a.x == r.d.x && trans.a.y == r.d.y && trans.a.z == r.d.z; }
 // may this BVH be searched out of the reference's order for this pair of rays?  (through an instance the triangles see a
 // re-normalised direction, so hit t and box-entry t are in different units; pruning stays conservative only if the local direction
@@ -686,8 +820,15 @@ __device__ __forceinline__ int accelClosestImpl(const DScene& S, int kind, int i
           const int got = one ? leanClosest<true, DRT_FSTACK>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc) : leanClosest<false, DRT_FSTACK>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc);
           if (got < 0) { flagError(1u); return 0; }
           return got;
-        } else if constexpr ((F & TF_LITERAL1) != 0) return leanClosest<false, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc);
-        else { if (!one) return -1; return leanClosest<true, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc); }
+        } else {
+#if DRT_LEAN32
+          if constexpr ((F & TF_LITERAL1) != 0) return leanClosest32<DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out);
+          else { if (!one) return -1; return leanClosest32<DRT_LSTACK>(S, B, trans.o, trans.a, trans.o, trans.a, _ray.d, out); }      // flat scenes: one ray, one register set
+#else
+          if constexpr ((F & TF_LITERAL1) != 0) return leanClosest<false, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc);
+          else { if (!one) return -1; return leanClosest<true, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc); }
+#endif
+        }
       }
 #endif
       if constexpr (!NONLEAN) return -1;
@@ -827,8 +968,15 @@ __device__ __forceinline__ int accelShadowImpl(const DScene& S, int kind, int id
         const int got = one ? leanShadow<true, DRT_FSTACK>(S, B, trans.o, trans.a, r.o, r.d, dist, tc) : leanShadow<false, DRT_FSTACK>(S, B, trans.o, trans.a, r.o, r.d, dist, tc);
         if (got < 0) { flagError(1u); return 0; }
         return got;
-      } else if constexpr ((F & TF_LITERAL1) != 0) return leanShadow<false, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, dist, tc);
-      else { if (!one) return -1; return leanShadow<true, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, dist, tc); }
+      } else {
+#if DRT_LEAN32
+        if constexpr ((F & TF_LITERAL1) != 0) return leanShadow32<DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, dist);
+        else { if (!one) return -1; return leanShadow32<DRT_LSTACK>(S, B, trans.o, trans.a, trans.o, trans.a, dist); }
+#else
+        if constexpr ((F & TF_LITERAL1) != 0) return leanShadow<false, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, dist, tc);
+        else { if (!one) return -1; return leanShadow<true, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, dist, tc); }
+#endif
+      }
     }
 #endif
     if constexpr (!NONLEAN) return -1;

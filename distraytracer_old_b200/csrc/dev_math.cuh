@@ -74,7 +74,7 @@ struct DScene {
   const FInstance* instances; const FList* lists; const FBvh* bvhs; const FNode* nodes; const FLight* lights;
   const FShader* shaders; const FTexture* textures; const double* texColors; const FImage* images; const int32_t* texels;
   // fast-BVH view: packed triangles and the node array their fastRoot indexes (== nodes, or the GPU-built LBVH nodes); accelMode = drt.h DRT_ACCEL_*
-  const FTri* tris; const FNode* fnodes; int32_t accelMode; int32_t padA;
+  const FTri* tris; const FNode* fnodes; const FNode32* fnodes32; int32_t accelMode; int32_t padA;
   // photon map (hash grid), see photon kernels
   const double* phPos; const double* phPwr; const uint32_t* cellStart; const uint32_t* cellEnd; uint32_t gridDim[3]; uint32_t numPhotons; double gridMin[3]; double cellSize;
   FGlobals g;

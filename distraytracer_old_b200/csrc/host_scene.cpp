@@ -1,5 +1,6 @@
 // `.cli` interpreter + scene flattener (see host_scene.h for the reference map).
 #include "host_scene.h"
+#include <cmath>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -577,6 +578,17 @@ void HostScene::finalize() {
     if (code >= 0) prims[r.idx].pad0 = code >> 3;
   }
   g.numTop = (int)top.size(); g.numLights = (int)lights.size();
+  // FP32 mirror of every node (round to nearest) and, per fast BVH, the largest |coordinate| of its node boxes per axis
+  nodes32.resize(nodes.size());
+  for (size_t i = 0; i < nodes.size(); ++i) { const FNode& n = nodes[i]; FNode32& m = nodes32[i];
+    for (int k = 0; k < 3; ++k) { m.lmin[k] = (float)n.lmin[k]; m.lmax[k] = (float)n.lmax[k]; m.rmin[k] = (float)n.rmin[k]; m.rmax[k] = (float)n.rmax[k]; }
+    m.left = n.left; m.right = n.right; m.triL = n.triL; m.triR = n.triR; }
+  for (FBvh& B : bvhs) { B.absMax[0] = B.absMax[1] = B.absMax[2] = 0; B.pad2 = 0; if (!B.fast || B.root < 0) continue;
+    std::vector<int32_t> st{B.root};
+    while (!st.empty()) { const FNode& n = nodes[st.back()]; st.pop_back();
+      for (int k = 0; k < 3; ++k) { const double m = std::max(std::max(std::fabs(n.lmin[k]), std::fabs(n.lmax[k])), std::max(std::fabs(n.rmin[k]), std::fabs(n.rmax[k])));
+        const float f = (float)m; B.absMax[k] = std::max(B.absMax[k], f >= m ? f : std::nextafter(f, INFINITY)); }
+      if (n.left >= 0) st.push_back(n.left); if (n.right >= 0) st.push_back(n.right); } }
 }
 
 void HostScene::dumpNode(int32_t ref, std::vector<int32_t>& out) const {

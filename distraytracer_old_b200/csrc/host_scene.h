@@ -47,6 +47,7 @@ class HostScene {
   std::vector<FList> lists;
   std::vector<FBvh> bvhs;
   std::vector<FNode> nodes;
+  std::vector<FNode32> nodes32;       // FP32 mirror of `nodes` (built by finalize)
   std::vector<FTri> tris;             // packed triangles of the fast BVHs (see scene_flat.h)
   std::vector<FLight> lights;
   std::vector<FShader> shaders;

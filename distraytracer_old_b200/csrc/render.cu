@@ -390,6 +390,14 @@ __global__ void k_finish(const __grid_constant__ DScene S, PixMap pm, long long 
   }
 }
 
+// FP32 mirror of GPU-built nodes (DRT_ACCEL_LBVH); host-built nodes are mirrored by the flattener
+__global__ void k_nodes32(const FNode* __restrict__ in, long long n, FNode32* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+  const FNode a = in[i]; FNode32 m;
+  for (int k = 0; k < 3; ++k) { m.lmin[k] = (float)a.lmin[k]; m.lmax[k] = (float)a.lmax[k]; m.rmin[k] = (float)a.rmin[k]; m.rmax[k] = (float)a.rmax[k]; }
+  m.left = a.left; m.right = a.right; m.triL = a.triL; m.triR = a.triR; out[i] = m;
+}
+
 // parity helpers ------------------------------------------------------------------------------------------------
 template <bool COUNT>
 __global__ void k_trace_explicit(const __grid_constant__ DScene S, long long n, const double* __restrict__ org, const double* __restrict__ dir, int32_t* __restrict__ ids, double* __restrict__ tOut) {
@@ -449,7 +457,7 @@ struct SceneArena {
 };
 
 struct Renderer::Impl {
-  DScene ds; SceneArena arena; DBuf<FNode> lbvhNodeBuf; DBuf<FTri> lbvhTriBuf; LbvhScratch lbvhScratch;
+  DScene ds; SceneArena arena; DBuf<FNode> lbvhNodeBuf; DBuf<FNode32> lbvhNode32Buf; DBuf<FTri> lbvhTriBuf; LbvhScratch lbvhScratch;
   DBuf<RayRec> rays[2]; DBuf<Hit> hits; DBuf<Hit> hits0; DBuf<SurfRec> surf; DBuf<NodeRec> nodes; Counters* ctr = nullptr; Counters* ctrHost = nullptr;
   DBuf<uint32_t> deferT, deferL;                 // deferral lists of the lean trace / light kernels (ray indices of one level)
   std::vector<cudaEvent_t> evPool;               // stage timing of a whole frame without a host sync per level
@@ -482,7 +490,7 @@ Renderer::Renderer(int device) : impl_(new Impl), device_(device) {
 }
 Renderer::~Renderer() {
   cudaSetDevice(device_);
-  impl_->arena.release(); impl_->lbvhNodeBuf.release(); impl_->lbvhTriBuf.release(); impl_->lbvhScratch.release();
+  impl_->arena.release(); impl_->lbvhNodeBuf.release(); impl_->lbvhNode32Buf.release(); impl_->lbvhTriBuf.release(); impl_->lbvhScratch.release();
   impl_->rays[0].release(); impl_->rays[1].release(); impl_->hits.release(); impl_->hits0.release(); impl_->surf.release(); impl_->nodes.release();
   impl_->oArgb.release(); impl_->oPrim.release(); impl_->oInst.release(); impl_->oRgb.release(); impl_->oT.release();
   impl_->deferT.release(); impl_->deferL.release(); for (auto& e : impl_->evPool) cudaEventDestroy(e);
@@ -509,13 +517,16 @@ void Renderer::upload(const HostScene& hs, bool sameScene) {
   // DRT_ACCEL_LBVH: every qualifying pure-triangle BVH is rebuilt on the GPU (lbvh.cuh) after the copy. Node slots: the reference nodes
   // first (instance-level trees, BVHs that do not qualify, rays whose units forbid reordering keep using them), LBVH nodes appended.
   size_t extra = 0;
-  if (d.accelMode == 2) for (FBvh& B : bv) if (B.fast && B.triXform == B.xform && B.triCount > 4) { B.fastRoot = (int32_t)(hs.nodes.size() + extra); extra += (size_t)((B.triCount + 3) / 4 - 1); }
+  if (d.accelMode == 2) for (FBvh& B : bv) if (B.fast && B.triXform == B.xform && B.triCount > 4) { B.fastRoot = (int32_t)(hs.nodes.size() + extra); extra += (size_t)((B.triCount + 3) / 4 - 1);
+    // LBVH node boxes are unions of the triangles' own boxes padded by 1e-12: bound them by the vertices
+    for (int k = 0; k < 3; ++k) { double m = 0; for (int t = B.triStart; t < B.triStart + B.triCount; ++t) for (int v = 0; v < 3; ++v) m = std::max(m, std::fabs(hs.tris[t].v[3 * v + k]));
+      B.absMax[k] = (float)(m * (1.0 + 1e-6) + 1e-9); } }
   A.reserve(SceneArena::need(hs.xforms) + SceneArena::need(hs.prims) + SceneArena::need(hs.pdata) + SceneArena::need(hs.top) + SceneArena::need(hs.children) + SceneArena::need(hs.instances) +
-            SceneArena::need(hs.lists) + SceneArena::need(hs.nodes) + SceneArena::need(hs.tris) + SceneArena::need(bv) + SceneArena::need(hs.lights) + SceneArena::need(hs.shaders) +
+            SceneArena::need(hs.lists) + SceneArena::need(hs.nodes) + SceneArena::need(hs.nodes32) + SceneArena::need(hs.tris) + SceneArena::need(bv) + SceneArena::need(hs.lights) + SceneArena::need(hs.shaders) +
             SceneArena::need(hs.textures) + SceneArena::need(hs.texColors) + SceneArena::need(hs.images) + SceneArena::need(hs.texels) + 4096, st);
   A.begin();
   d.xforms = A.put(hs.xforms); d.prims = A.put(hs.prims); d.pdata = A.put(hs.pdata); d.top = A.put(hs.top); d.children = A.put(hs.children); d.instances = A.put(hs.instances);
-  d.lists = A.put(hs.lists); d.nodes = A.put(hs.nodes); d.tris = A.put(hs.tris); d.bvhs = A.put(bv); d.lights = A.put(hs.lights); d.shaders = A.put(hs.shaders);
+  d.lists = A.put(hs.lists); d.nodes = A.put(hs.nodes); d.fnodes32 = A.put(hs.nodes32); d.tris = A.put(hs.tris); d.bvhs = A.put(bv); d.lights = A.put(hs.lights); d.shaders = A.put(hs.shaders);
   d.textures = A.put(hs.textures); d.texColors = A.put(hs.texColors); d.images = A.put(hs.images); d.texels = A.put(hs.texels);
   A.flush(st);
   d.fnodes = d.nodes; impl_->lbvhMs = 0; impl_->lbvhTris = 0; impl_->lbvhNodes = 0;
@@ -533,7 +544,10 @@ void Renderer::upload(const HostScene& hs, bool sameScene) {
       impl_->lbvhTris += B.triCount; impl_->lbvhNodes += wrote;
     }
     CK(cudaEventRecord(impl_->ev[7], st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError()); CK(cudaEventElapsedTime(&impl_->lbvhMs, impl_->ev[6], impl_->ev[7]));
-    d.fnodes = ln; d.tris = lt;
+    impl_->lbvhNode32Buf.ensure(n0 + extra, st);
+    k_nodes32<<<(unsigned)((n0 + extra + 255) / 256), 256, 0, st>>>(ln, (long long)(n0 + extra), impl_->lbvhNode32Buf.p); ++g_kernelLaunches;
+    CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+    d.fnodes = ln; d.fnodes32 = impl_->lbvhNode32Buf.p; d.tris = lt;
   }
   // Kernel variant for this scene shape (dev_isect.cuh TF_*).  Only a speed choice: whatever a lean variant cannot serve is deferred, ray by
   // ray, to the generic kernels, which implement the same rules.

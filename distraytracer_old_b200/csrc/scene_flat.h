@@ -43,11 +43,16 @@ struct FList { int32_t xform, childStart, childCount, pad; double bmin[3], bmax[
 // "fast" BVHs (every leaf holds only triangles that share one CTM) additionally own a contiguous run of packed triangle records
 // (FTri, DFS leaf order) and tri-leaf codes in their nodes; fastRoot indexes DScene::fnodes (the same nodes in reference-topology
 // modes, the GPU-built LBVH nodes in DRT_ACCEL_LBVH mode).
-struct FBvh { int32_t xform, root, nodeCount, dropped; double bmin[3], bmax[3]; int32_t fast, triXform, triHitXform, fastRoot, triStart, triCount, pad0, pad1; };
+// absMax: per-axis bound of |coordinate| over every node box the fast descent can load (error budget of the FP32 pre-test, dev_isect.cuh)
+struct FBvh { int32_t xform, root, nodeCount, dropped; double bmin[3], bmax[3]; int32_t fast, triXform, triHitXform, fastRoot, triStart, triCount, pad0, pad1; float absMax[3]; int32_t pad2; };
 
 // inner node with both child boxes; child >= 0 inner node, child < 0 -> ~list index. 128 B, 16 B aligned (128-bit loads).
 // triL / triR: when the child is a pure-triangle leaf of a fast BVH, (first FTri index << 3) | count ; else -1.
 struct alignas(16) FNode { double lmin[3], lmax[3], rmin[3], rmax[3]; int32_t left, right, triL, triR; int32_t pad2[4]; };
+
+// FP32 mirror of an FNode (same index): both child boxes rounded to nearest float + the links.  64 B = 4 x 128-bit loads.  The lean descent
+// decides a box on these when the decision is certain under a rigorous error bound and reads the FP64 node only when it is not.
+struct alignas(16) FNode32 { float lmin[3], lmax[3], rmin[3], rmax[3]; int32_t left, right, triL, triR; };
 
 // packed triangle of a fast BVH, 128 B, read with 8 x 128-bit loads. Winding state 0 as given; state 1 (myPlanarObject.invertNormal,
 // :71-88) = vertices in reverse order, normal -N (bitwise), plane offset Drev (formed from the reversed first vertex, so stored).

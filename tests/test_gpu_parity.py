@@ -37,10 +37,11 @@ def check_scene(drt, orc, make, name, cols=300, rows=300, spp=0, photons=-1, sto
         assert psnr(rgb8(orc, g["argb"]), rgb8(orc, r["argb"])) >= 40.0
     st = g["stats"]
     assert st.rays_primary == r["stats"]["primary"]
-    assert abs(int(st.rays_shadow) - r["stats"]["shadow"]) <= max(2, TIE_BUDGET * r["stats"]["shadow"])
     # the "simple" shader spawns a ray whenever its Fresnel weight is > 0 (myObjShader.java:584,613): weights of 1e-34 vs exactly 0 depend on
-    # the last ulp of sin(acos(x)) (glibc vs CUDA libm), so ray COUNTS may differ there while their contribution is nil
+    # the last ulp of sin(acos(x)) (glibc vs CUDA libm), so ray COUNTS (and the shadow rays of the hits those rays make) may differ there while
+    # their contribution is nil
     tol = 0.25 if name in SIMPLE_SHADER_SCENES else 1e-3
+    assert abs(int(st.rays_shadow) - r["stats"]["shadow"]) <= max(2, (0.05 if name in SIMPLE_SHADER_SCENES else TIE_BUDGET) * r["stats"]["shadow"])
     assert abs(int(st.rays_reflect) - r["stats"]["reflect"]) <= max(2, tol * r["stats"]["reflect"])
     assert abs(int(st.rays_refract) - r["stats"]["refract"]) <= max(2, tol * r["stats"]["refract"])
     assert st.kernel_launches > 0
@@ -48,7 +49,7 @@ def check_scene(drt, orc, make, name, cols=300, rows=300, spp=0, photons=-1, sto
     return g, r
 
 
-SIMPLE_SHADER_SCENES = {"c2clear"}
+SIMPLE_SHADER_SCENES = {"c2clear", "old_t07a", "trTransFish"}      # `shiny` with ktrans > 0: the "simple" refraction shader
 
 DETERMINISTIC = ["t01", "t02", "t03", "t06", "t07", "t09", "p3_t01", "p3_t02", "p3_t03", "p3_t04", "p3_t05", "p3_t06", "p3_t07", "p3_t08", "p3_t12",
                  "p3_t02_sierp", "c2clear", "c3shinyBall", "c3spotLight", "c5Fish", "c6", "c6Fish", "cylinder1", "old_t07c", "trTrans", "p2_t01", "p2_t03", "p2_t05", "p2_t07",
