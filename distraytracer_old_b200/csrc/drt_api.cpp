@@ -101,6 +101,18 @@ int drt_render_device_chunks(drt_ctx* ctx, int32_t world, int32_t rank, int32_t 
     ctx->renderer->renderChunks(0, 0, world, rank, chunk_rows, o, &rs); toStats(rs, stats); }, DRT_ERR_CUDA)
 }
 
+int drt_comm_unique_id(uint8_t* id128) { if (!id128) return DRT_ERR_BAD_ARG; try { Renderer::commUniqueId(id128); return DRT_OK; } catch (std::exception& e) { fprintf(stderr, "drt_comm_unique_id: %s\n", e.what()); return DRT_ERR_CUDA; } }
+int drt_comm_init(drt_ctx* ctx, const uint8_t* id128, int32_t world, int32_t rank) { NEED_DEV(ctx) GUARD(ctx, { if (!id128 && world > 1) throw std::runtime_error("null id"); unsigned char z[128] = {0}; ctx->renderer->commInit(id128 ? id128 : z, world, rank); }, DRT_ERR_CUDA) }
+int drt_comm_destroy(drt_ctx* ctx) { NEED_DEV(ctx) GUARD(ctx, ctx->renderer->commDestroy(), DRT_ERR_CUDA) }
+int drt_render_distributed(drt_ctx* ctx, int32_t* argb_host, int32_t* argb_dev, int32_t chunk_rows, int32_t reemit, drt_stats* stats) {
+  NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized) throw std::runtime_error("scene not finalized"); RenderStats rs; std::memset(&rs, 0, sizeof(rs));
+    ctx->renderer->renderDistributed(argb_host, argb_dev, chunk_rows, reemit != 0, &rs); toStats(rs, stats); }, DRT_ERR_CUDA)
+}
+
+int64_t drt_dist_rank_pixels(int32_t cols, int32_t rows, int32_t world, int32_t rank, int32_t chunk_rows) { if (cols < 1 || rows < 1 || world < 1 || rank < 0 || rank >= world || chunk_rows < 1) return DRT_ERR_BAD_ARG; return Renderer::distRankPixels(cols, rows, world, rank, chunk_rows); }
+int64_t drt_dist_abs_pixel(int32_t cols, int32_t rows, int32_t world, int32_t rank, int32_t chunk_rows, int64_t compact) { if (cols < 1 || rows < 1 || world < 1 || rank < 0 || rank >= world || chunk_rows < 1 || compact < 0) return DRT_ERR_BAD_ARG; return Renderer::distAbsPixel(cols, rows, world, rank, chunk_rows, compact); }
+int drt_dist_photon_range(int64_t n, int32_t world, int32_t rank, int64_t* out2) { if (!out2 || world < 1 || rank < 0 || rank >= world || n < 0) return DRT_ERR_BAD_ARG; long long o[2]; Renderer::distPhotonRange(n, world, rank, o); out2[0] = o[0]; out2[1] = o[1]; return DRT_OK; }
+
 // PNG (8-bit RGB, zlib deflate) -- PImage.save of an RGB image
 int drt_save_png(const char* path, const int32_t* argb, int32_t cols, int32_t rows) {
   if (!path || !argb || cols <= 0 || rows <= 0) return DRT_ERR_BAD_ARG;

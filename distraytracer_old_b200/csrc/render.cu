@@ -380,7 +380,7 @@ __global__ void k_finish(const __grid_constant__ DScene S, PixMap pm, long long 
   D3 c;
   if (S.g.spp < 1) c = d3(0, 0, 0);
   else c = clampColor1(d3(r / spp, g / spp, b / spp));
-  if (out.argb) out.argb[q] = packArgb(c);
+  if (out.argb) out.argb[out.packed ? (pix0 + p) : q] = packArgb(c);
   if (out.rgb) { out.rgb[3 * q] = c.x; out.rgb[3 * q + 1] = c.y; out.rgb[3 * q + 2] = c.z; }
   if (out.hitPrim || out.hitInst || out.t) {
     const Hit h = hits0[p * spp];
@@ -762,6 +762,120 @@ void Renderer::evalTexture(int shaderIdx, long long n, const double* hitLocHost,
   k_eval_texture<<<gridFor(n, 128), 128, 0, st>>>(impl_->ds, shaderIdx, n, a, b, c);
   CK(cudaMemcpyAsync(outHost, c, n * 24, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
   cudaFree(a); cudaFree(b); cudaFree(c);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-GPU inside the library: one context per GPU, the frame split in interleaved row chunks, photon emission split by
+// photon index.  The only exchanges are an all-gather of photon records and a gather of finished chunks to rank 0, both NCCL calls on the
+// renderer's own stream.  NCCL is bound at run time (dlopen): a single-GPU host never needs it.
+// ---------------------------------------------------------------------------------------------------------------
+}  // namespace drt
+#include <dlfcn.h>
+#include <nccl.h>
+namespace drt {
+
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr; ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr; ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr; ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr; ncclResult_t (*GroupEnd)() = nullptr; const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi& nccl() {
+  static NcclApi a;
+  if (!a.h) {
+    const char* names[] = {getenv("DRT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { if (!n) continue; a.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (a.h) break; }
+    if (!a.h) throw std::runtime_error(std::string("NCCL not found (libnccl.so.2): multi-GPU rendering needs it: ") + dlerror());
+    auto sym = [&](const char* n) { void* p = dlsym(a.h, n); if (!p) throw std::runtime_error(std::string("NCCL symbol missing: ") + n); return p; };
+    a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId"); a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank"); a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+    a.Send = (decltype(a.Send))sym("ncclSend"); a.Recv = (decltype(a.Recv))sym("ncclRecv"); a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
+    a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart"); a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd"); a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+  }
+  return a;
+}
+#define NK(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) throw std::runtime_error(std::string("NCCL error: ") + nccl().GetErrorString(r_) + " at " #x); } while (0)
+
+void Renderer::commUniqueId(unsigned char id128[128]) { static_assert(sizeof(ncclUniqueId) == 128, "id size"); ncclUniqueId id; NK(nccl().GetUniqueId(&id)); std::memcpy(id128, &id, 128); }
+void Renderer::commInit(const unsigned char id128[128], int world, int rank) {
+  if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("bad world / rank");
+  commDestroy(); world_ = world; rank_ = rank;
+  if (world == 1) return;
+  CK(cudaSetDevice(device_)); ncclUniqueId id; std::memcpy(&id, id128, 128); ncclComm_t c = nullptr;
+  NK(nccl().CommInitRank(&c, world, id, rank)); comm_ = c;
+}
+void Renderer::commDestroy() { if (comm_) { cudaSetDevice(device_); nccl().CommDestroy((ncclComm_t)comm_); comm_ = nullptr; } world_ = 1; rank_ = 0; }
+
+// chunk c of rank r (compact slot j = c * chunkPix + within) -> absolute pixel ((c * world + r) * chunkPix + within)
+__global__ void k_unpack_chunks(const int32_t* __restrict__ staging, long long perRankPix, int world, long long chunkPix, long long totalPix, int32_t* __restrict__ frame) {
+  const long long n = perRankPix * (world - 1);
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    const int r = 1 + (int)(k / perRankPix); const long long j = k % perRankPix, c = j / chunkPix, within = j % chunkPix;
+    const long long q = (c * world + r) * chunkPix + within;
+    if (q < totalPix) frame[q] = staging[(long long)(r - 1) * perRankPix + j];
+  }
+}
+__global__ void k_store_u64(unsigned long long* dst, unsigned long long v) { *dst = v; }
+
+long long Renderer::distRankPixels(int cols, int rows, int world, int rank, int chunkRows) {
+  const long long nChunks = (rows + chunkRows - 1) / chunkRows; return ((nChunks - rank + world - 1) / world) * (long long)chunkRows * cols;
+}
+long long Renderer::distAbsPixel(int cols, int rows, int world, int rank, int chunkRows, long long compact) {
+  PixMap pm; pm.totalPix = (long long)cols * rows; pm.world = world; pm.rank = rank; pm.chunkPix = (world == 1) ? std::max<long long>(pm.totalPix, 1) : (long long)chunkRows * cols;
+  const long long q = absPixel(pm, compact); return q < pm.totalPix ? q : -1;
+}
+void Renderer::distPhotonRange(long long nCast, int world, int rank, long long out2[2]) { out2[0] = nCast * rank / world; out2[1] = nCast * (rank + 1) / world; }
+
+void Renderer::renderDistributed(int32_t* argbHostRank0, int32_t* argbDevRank0, int chunkRows, bool reemitPhotons, RenderStats* stats) {
+  CK(cudaSetDevice(device_)); cudaStream_t st = (cudaStream_t)stream_; Impl& I = *impl_;
+  const int world = world_, rank = rank_; if (chunkRows < 1) chunkRows = 8;
+  if (world > 1 && !comm_) throw std::runtime_error("drt_comm_init has not been called on this context");
+  const long long totalPix = (long long)g_.cols * g_.rows, chunkPix = (long long)chunkRows * g_.cols;
+  const long long nChunks = (g_.rows + chunkRows - 1) / chunkRows, perRankChunks = (nChunks + world - 1) / world, perRankPix = perRankChunks * chunkPix;
+  auto chunksOf = [&](int r) { return distRankPixels(g_.cols, g_.rows, world, r, chunkRows) / chunkPix; };
+  unsigned long long photonLaunches = 0; float msPhoton = 0;
+  // ---- photon pass: rank r emits photon indices [r N / world, (r+1) N / world) of every light; canonical-order records are all-gathered
+  //      (counts first, blocks padded to the longest) and every rank builds the full grid: bit-identical to the single-GPU map
+  if (g_.photonKind != 0 && (reemitPhotons || !I.photons.built)) {
+    const unsigned long long l0 = g_kernelLaunches; cudaEvent_t e0 = I.pev(0), e1 = I.pev(1); CK(cudaEventRecord(e0, st));
+    long long pr[2]; distPhotonRange(g_.numPhotonsCast, world, rank, pr); const long long i0 = pr[0], i1 = pr[1];
+    devErrorReset(st); I.photons.emitRange(I.ds, i0, i1, I.ctr, I.ctrHost, st); devErrorCheck(st);
+    if (world > 1) {
+      unsigned long long* cnt = nullptr; CK(cudaMalloc(&cnt, sizeof(unsigned long long) * (world + 1)));
+      k_store_u64<<<1, 1, 0, st>>>(cnt + world, I.photons.count);
+      NK(nccl().AllGather(cnt + world, cnt, 1, ncclUint64, (ncclComm_t)comm_, st));
+      std::vector<unsigned long long> counts(world); CK(cudaMemcpyAsync(counts.data(), cnt, sizeof(unsigned long long) * world, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); cudaFree(cnt);
+      unsigned long long mx = 1, total = 0, segs = I.photons.segments; for (auto c : counts) { mx = std::max(mx, c); total += c; }
+      PhotonRec *mine = nullptr, *all = nullptr; CK(cudaMalloc(&mine, mx * sizeof(PhotonRec))); CK(cudaMalloc(&all, mx * world * sizeof(PhotonRec)));
+      CK(cudaMemsetAsync(mine, 0, mx * sizeof(PhotonRec), st));
+      if (I.photons.count) CK(cudaMemcpyAsync(mine, I.photons.rec, I.photons.count * sizeof(PhotonRec), cudaMemcpyDeviceToDevice, st));
+      NK(nccl().AllGather(mine, all, mx * sizeof(PhotonRec), ncclChar, (ncclComm_t)comm_, st));
+      I.photons.built = false; I.photons.emitted = true; I.photons.count = 0; I.photons.ensureRec((size_t)total, st);
+      unsigned long long at = 0; for (int r = 0; r < world; ++r) { if (counts[r]) CK(cudaMemcpyAsync(I.photons.rec + at, all + (size_t)r * mx, counts[r] * sizeof(PhotonRec), cudaMemcpyDeviceToDevice, st)); at += counts[r]; }
+      I.photons.count = total; I.photons.segments = segs; CK(cudaStreamSynchronize(st)); cudaFree(mine); cudaFree(all);
+    }
+    I.photons.buildGrid(I.ds, st);
+    CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st)); CK(cudaEventElapsedTime(&msPhoton, e0, e1)); photonLaunches = g_kernelLaunches - l0;
+  }
+  // ---- this rank's chunks: rank 0 renders in place into the frame, the others into a compact buffer that is sent as one message
+  RenderOutputs o; std::memset(&o, 0, sizeof(o)); RenderStats rs; std::memset(&rs, 0, sizeof(rs));
+  if (rank == 0) { if (argbDevRank0) o.argb = argbDevRank0; else { I.oArgb.ensure((size_t)(perRankPix * world), st); o.argb = I.oArgb.p; } }
+  else { I.oArgb.ensure((size_t)perRankPix, st); o.argb = I.oArgb.p; o.packed = 1; }
+  if (world == 1) renderChunks(0, totalPix, 1, 0, 0, o, &rs); else renderChunks(0, 0, world, rank, chunkRows, o, &rs);
+  if (world > 1) {
+    if (rank == 0) {
+      I.oPrim.ensure((size_t)(perRankPix * (world - 1)), st);        // staging for the other ranks' compact buffers
+      NK(nccl().GroupStart());
+      for (int r = 1; r < world; ++r) NK(nccl().Recv(I.oPrim.p + (size_t)(r - 1) * perRankPix, (size_t)(chunksOf(r) * chunkPix), ncclInt32, r, (ncclComm_t)comm_, st));
+      NK(nccl().GroupEnd());
+      k_unpack_chunks<<<(unsigned)std::min<long long>((perRankPix * (world - 1) + 255) / 256, 148 * 16), 256, 0, st>>>(I.oPrim.p, perRankPix, world, chunkPix, totalPix, o.argb); ++rs.kernelLaunches;
+    } else NK(nccl().Send(o.argb, (size_t)(chunksOf(rank) * chunkPix), ncclInt32, 0, (ncclComm_t)comm_, st));
+  }
+  if (rank == 0 && argbHostRank0) CK(cudaMemcpyAsync(argbHostRank0, o.argb, (size_t)totalPix * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+  rs.kernelLaunches += photonLaunches; rs.msOther += msPhoton; rs.msTotal += msPhoton;
+  if (stats) *stats = rs;
 }
 
 }  // namespace drt

@@ -16,6 +16,7 @@ struct RenderStats {
 
 struct RenderOutputs {           // device pointers, any may be null; sized cols*rows (rgb: 3x)
   int32_t* argb; int32_t* hitPrim; int32_t* hitInst; double* rgb; double* t;
+  int32_t packed;                // != 0: argb is indexed by the rank's COMPACT pixel index (its chunks back to back) instead of the absolute pixel
 };
 
 class Renderer {
@@ -40,6 +41,19 @@ class Renderer {
   long long exportPhotonsDevice(double* dst6Dev, long long cap);                  // canonical-order records -> caller's device buffer; returns count
   void buildPhotonsFromDevice(const double* src6Dev, long long n, RenderStats* stats);   // replace the record set (e.g. all-gathered) and build the grid
   void probePhotons(long long n, const double* ptsHost, double* out5Host);       // per point: sum r,g,b of the k nearest, d^2 of the farthest, candidates visited
+  // ---- multi-GPU inside the library: one Renderer per rank, NCCL (loaded at run time) on the renderer's own stream
+  static void commUniqueId(unsigned char id128[128]);
+  void commInit(const unsigned char id128[128], int world, int rank);
+  void commDestroy();
+  int commWorld() const { return world_; }
+  int commRank() const { return rank_; }
+  // this rank's interleaved row chunks -> NCCL send/recv gather -> assembled frame on rank 0 (device and/or host buffer; both may be null on
+  // other ranks).  Photon scenes: emission split by photon index, records all-gathered, grid built on every rank.
+  // the partition itself (pure host functions, also behind the C ABI so that the world-size-2 CPU tests exercise the shipped mapping)
+  static long long distRankPixels(int cols, int rows, int world, int rank, int chunkRows);                 // compact pixels rank `rank` renders (whole chunks)
+  static long long distAbsPixel(int cols, int rows, int world, int rank, int chunkRows, long long compact);   // absolute pixel of a compact slot, -1 beyond the frame
+  static void distPhotonRange(long long nCast, int world, int rank, long long out2[2]);
+  void renderDistributed(int32_t* argbHostRank0, int32_t* argbDevRank0, int chunkRows, bool reemitPhotons, RenderStats* stats);
   void accelInfo(double out[4]) const;                 // LBVH build ms (CUDA events), triangles and nodes it covers, scene bytes in HBM
   int cols() const { return g_.cols; }
   int rows() const { return g_.rows; }
@@ -57,6 +71,7 @@ class Renderer {
   bool counters_ = false;
   int traceMode_ = 0;
   bool keepDepthHint_ = false;
+  void* comm_ = nullptr; int world_ = 1, rank_ = 0;
 };
 
 }  // namespace drt

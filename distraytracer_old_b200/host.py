@@ -86,6 +86,13 @@ def load_library():
         "drt_photons_export_device": (i64, [vp, vp, i64]),
         "drt_photons_build_device": (C.c_int, [vp, vp, i64, C.POINTER(Stats)]),
         "drt_photon_probe": (C.c_int, [vp, i64, vp, vp]),
+        "drt_comm_unique_id": (C.c_int, [vp]),
+        "drt_comm_init": (C.c_int, [vp, vp, i32, i32]),
+        "drt_comm_destroy": (C.c_int, [vp]),
+        "drt_render_distributed": (C.c_int, [vp, vp, vp, i32, i32, C.POINTER(Stats)]),
+        "drt_dist_rank_pixels": (i64, [i32, i32, i32, i32, i32]),
+        "drt_dist_abs_pixel": (i64, [i32, i32, i32, i32, i32, i64]),
+        "drt_dist_photon_range": (C.c_int, [i64, i32, i32, C.POINTER(i64)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -99,7 +106,9 @@ EXPORTS = ["drt_create", "drt_destroy", "drt_last_error", "drt_set_image_loader"
            "drt_scene_command", "drt_scene_load_cli", "drt_scene_override", "drt_scene_finalize", "drt_scene_reupload",
            "drt_scene_info", "drt_scene_counts", "drt_accel_info", "drt_emit_photons", "drt_render", "drt_render_aov", "drt_render_device", "drt_render_device_chunks", "drt_save_png",
            "drt_trace_rays", "drt_eval_texture", "drt_dump_bvh", "drt_obj_ctm", "drt_sample_u01", "drt_get_photons",
-           "drt_emit_photons_range", "drt_photons_export_device", "drt_photons_build_device", "drt_photon_probe"]
+           "drt_emit_photons_range", "drt_photons_export_device", "drt_photons_build_device", "drt_photon_probe",
+           "drt_comm_unique_id", "drt_comm_init", "drt_comm_destroy", "drt_render_distributed",
+           "drt_dist_rank_pixels", "drt_dist_abs_pixel", "drt_dist_photon_range"]
 
 
 def decode_image_argb(path):
@@ -143,6 +152,19 @@ class Context:
     def _ck(self, rc):
         if rc != 0:
             raise DrtError("drt error %d: %s" % (rc, (self.L.drt_last_error(self.h) or b"").decode()))
+
+    # ---- multi-GPU inside the library (NCCL): rank 0 makes the id, the host ships it, every rank joins
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * 128)()
+        if load_library().drt_comm_unique_id(buf) != 0:
+            raise DrtError("drt_comm_unique_id failed (NCCL not available?)")
+        return bytes(buf)
+
+    def comm_init(self, id128, world, rank):
+        buf = (C.c_uint8 * 128).from_buffer_copy(id128) if id128 is not None else None
+        self._ck(self.L.drt_comm_init(self.h, buf, world, rank))
+        self.world, self.rank = world, rank
 
     def close(self):
         if getattr(self, "h", None):
@@ -233,6 +255,12 @@ class Scene:
     def draw_device_chunks(self, world, rank, chunk_rows, dev_ptr):
         st = Stats()
         self.ctx._ck(self.L.drt_render_device_chunks(self.ctx.h, world, rank, chunk_rows, dev_ptr, C.byref(st)))
+        return st
+
+    def draw_distributed(self, host_ptr=None, dev_ptr=None, chunk_rows=8, reemit_photons=False):
+        """Collective: this rank's chunks + NCCL gather; rank 0 receives the frame in host_ptr and / or dev_ptr (see include/drt.h)."""
+        st = Stats()
+        self.ctx._ck(self.L.drt_render_distributed(self.ctx.h, host_ptr, dev_ptr, chunk_rows, int(reemit_photons), C.byref(st)))
         return st
 
     def emit_photons(self):
@@ -337,6 +365,24 @@ class RTFileReader:
                     if out_dir:
                         scene.save(os.path.join(out_dir, os.path.splitext(tok[1])[0] + ".png"), argb)
         return scene
+
+
+def dist_rank_pixels(cols, rows, world, rank, chunk_rows=8):
+    return int(load_library().drt_dist_rank_pixels(cols, rows, world, rank, chunk_rows))
+
+
+def dist_abs_pixels(cols, rows, world, rank, chunk_rows=8):
+    """int64 array: absolute pixel of every compact slot of `rank` (-1 = padding), from the library's own mapping."""
+    L = load_library()
+    n = dist_rank_pixels(cols, rows, world, rank, chunk_rows)
+    return np.array([L.drt_dist_abs_pixel(cols, rows, world, rank, chunk_rows, j) for j in range(n)], dtype=np.int64)
+
+
+def dist_photon_range(n_cast, world, rank):
+    o = (C.c_int64 * 2)()
+    if load_library().drt_dist_photon_range(n_cast, world, rank, o) != 0:
+        raise DrtError("bad photon partition")
+    return int(o[0]), int(o[1])
 
 
 def sample_u01(seed, stream, a, b, c, d):

@@ -81,6 +81,21 @@ int drt_render_device(drt_ctx* ctx, int64_t pix0, int64_t pix1, int32_t* argb_de
 /* multi-GPU tiles: render this rank's interleaved row chunks (chunk c of the rank = rows [(c*world+rank)*chunk_rows, +chunk_rows)) at their
  * absolute positions of a full cols*rows DEVICE buffer; pixels of other ranks are left untouched */
 int drt_render_device_chunks(drt_ctx* ctx, int32_t world, int32_t rank, int32_t chunk_rows, int32_t* argb_dev, drt_stats* stats);
+/* ---- multi-GPU inside the library (no reference counterpart: the reference renders serially, myScene.java:1481-1531).  One context per GPU
+ * (one process per GPU, or several contexts in one host process on different threads).  Rank 0 creates an id, the host ships its 128 bytes
+ * to the other ranks by any transport, every rank calls drt_comm_init (collective).  drt_render_distributed (collective) renders this rank's
+ * interleaved row chunks, gathers them to rank 0 over NCCL (send / recv into the frame) and, for photon scenes, splits the emission by
+ * photon index, all-gathers the records and builds the grid on every rank.  The frame is bit-identical for every world size. */
+int drt_comm_unique_id(uint8_t* id128);
+int drt_comm_init(drt_ctx* ctx, const uint8_t* id128, int32_t world, int32_t rank);
+int drt_comm_destroy(drt_ctx* ctx);
+/* argb_host_rank0 / argb_dev_rank0: cols*rows ints on rank 0 (either may be NULL), ignored on other ranks.  reemit_photons != 0: redo the photon pass even if a map exists (the reference emits inside every draw) */
+int drt_render_distributed(drt_ctx* ctx, int32_t* argb_host_rank0, int32_t* argb_dev_rank0, int32_t chunk_rows, int32_t reemit_photons, drt_stats* stats);
+/* the partition behind drt_render_distributed as pure host functions (no device needed): compact pixels rank `rank` renders (whole chunks),
+ * absolute pixel of one of its compact slots (-1 = padding beyond the frame), photon index range [out2[0], out2[1]) it emits */
+int64_t drt_dist_rank_pixels(int32_t cols, int32_t rows, int32_t world, int32_t rank, int32_t chunk_rows);
+int64_t drt_dist_abs_pixel(int32_t cols, int32_t rows, int32_t world, int32_t rank, int32_t chunk_rows, int64_t compact_index);
+int drt_dist_photon_range(int64_t n_cast, int32_t world, int32_t rank, int64_t* out2);
 int drt_save_png(const char* path, const int32_t* argb, int32_t cols, int32_t rows);  /* PImage.save (myScene.java:1194) */
 
 /* ---- parity probes (used by tests; not needed by a host) ---- */

@@ -49,6 +49,8 @@ def lib():
         L.orc_photon_probe.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
         L.orc_render.restype = C.c_double
         L.orc_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
+        L.orc_render_chunks.restype = C.c_double
+        L.orc_render_chunks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_trace_rays.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_dump_bvh.restype = C.c_longlong
         L.orc_dump_bvh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
@@ -116,6 +118,14 @@ class OracleScene:
         res["stats"] = dict(zip(STAT_NAMES, [int(x) for x in st]))
         res["pixels"] = n
         return res
+
+    def render_chunks(self, chunk_rows, stride, phase=0, threads=1, want_argb=True):
+        """Interleaved row chunks {c : c % stride == phase}: the pixel set of GPU rank `phase` of `stride` (compact, chunks back to back)."""
+        n_chunks = len(range(phase, (self.rows + chunk_rows - 1) // chunk_rows, stride))
+        argb = np.zeros((n_chunks * chunk_rows, self.cols), dtype=np.int32) if want_argb else None
+        st = np.zeros(10, dtype=np.uint64)
+        secs = lib().orc_render_chunks(self.h, chunk_rows, stride, phase, threads, argb.ctypes.data if argb is not None else None, st.ctypes.data)
+        return {"argb": argb, "seconds": secs, "stats": dict(zip(STAT_NAMES, [int(x) for x in st]))}
 
     def trace_rays(self, org, dirs):
         org = np.ascontiguousarray(org, dtype=np.float64)

@@ -5,6 +5,7 @@
 #include "orc_scene.hpp"
 #include <chrono>
 #include <thread>
+#include <atomic>
 
 using namespace orc;
 
@@ -93,6 +94,31 @@ double orc_render(void* hv, int x0, int y0, int x1, int y1, int threads, int32_t
   (void)H;
   if (threads == 1) work(0);
   else { std::vector<std::thread> th; for (int i = 0; i < threads; ++i) th.emplace_back(work, i); for (auto& t : th) t.join(); }
+  double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) { Stats a; for (int i = 0; i < threads; ++i) a.add(h->copies[i]->stats);
+    stats[0] = a.primary; stats[1] = a.shadow; stats[2] = a.reflect; stats[3] = a.refract; stats[4] = a.photonSeg; stats[5] = a.boxTests; stats[6] = a.primTests; stats[7] = a.boxTestsPrimary; stats[8] = a.primTestsPrimary; stats[9] = a.photonsStored; }
+  return secs;
+}
+
+// Render the interleaved row chunks {c : c % chunkStride == chunkPhase} (chunkRows rows each) of the frame -- the pixel set a GPU rank with
+// world = chunkStride, rank = chunkPhase renders (bench.py uses it as the bounded whole-frame sample of the reference arm).  argb: compact,
+// chunks back to back, cols ints per row (may be NULL).  Rows are handed out dynamically to `threads` workers.  Returns wall seconds.
+double orc_render_chunks(void* hv, int chunkRows, int chunkStride, int chunkPhase, int threads, int32_t* argb, uint64_t* stats) {
+  OrcHandle* h = (OrcHandle*)hv;
+  if (threads < 1) threads = 1; if (chunkRows < 1) chunkRows = 1; if (chunkStride < 1) chunkStride = 1;
+  for (int i = 0; i < threads; ++i) { Scene* s = h->get(i); s->stats = Stats(); }
+  h->get(0)->initRender();
+  for (int i = 1; i < threads; ++i) { Scene* s = h->copies[i]; if (h->copies[0]->isPhtnMapRndrd) { s->photonTree = h->copies[0]->photonTree; s->isPhtnMapRndrd = true; } }
+  const int rows = h->copies[0]->sceneRows, cols = h->copies[0]->sceneCols;
+  std::vector<std::pair<int, int>> work;          // (absolute row, compact row)
+  { int compact = 0; for (int c = chunkPhase; c * chunkRows < rows; c += chunkStride) for (int r = 0; r < chunkRows; ++r, ++compact) if (c * chunkRows + r < rows) work.push_back({c * chunkRows + r, compact}); }
+  std::atomic<size_t> next{0};
+  auto t0 = std::chrono::steady_clock::now();
+  auto run = [&](int tid) { Scene* s = h->copies[tid];
+    for (size_t k = next.fetch_add(1); k < work.size(); k = next.fetch_add(1)) for (int col = 0; col < cols; ++col) {
+      Scene::PixelOut p = s->renderPixel(work[k].first, col); if (argb) argb[(size_t)work[k].second * cols + col] = p.argb; } };
+  if (threads == 1) run(0);
+  else { std::vector<std::thread> th; for (int i = 0; i < threads; ++i) th.emplace_back(run, i); for (auto& t : th) t.join(); }
   double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (stats) { Stats a; for (int i = 0; i < threads; ++i) a.add(h->copies[i]->stats);
     stats[0] = a.primary; stats[1] = a.shadow; stats[2] = a.reflect; stats[3] = a.refract; stats[4] = a.photonSeg; stats[5] = a.boxTests; stats[6] = a.primTests; stats[7] = a.boxTestsPrimary; stats[8] = a.primTestsPrimary; stats[9] = a.photonsStored; }

@@ -44,6 +44,31 @@ WORKER = textwrap.dedent("""
     assert empty.shape[0] == 0 and c0 == [0] * world
     if rank == 0:
         print("PHOTONS_OK")
+    # ---- the partition the LIBRARY uses (drt_render_distributed; pure host functions behind the C ABI): rank r fills its compact buffer, rank 0
+    #      receives every rank's buffer (what ncclSend / ncclRecv do on the GPUs) and unpacks it with the same mapping -> the identity frame
+    from distraytracer_old_b200 import host as H
+    for rows2, cols2, cr in ((37, 29, 8), (40, 16, 5), (7, 3, 8)):
+        idx = torch.from_numpy(H.dist_abs_pixels(cols2, rows2, world, rank, cr))
+        assert idx.numel() == H.dist_rank_pixels(cols2, rows2, world, rank, cr)
+        mine = torch.where(idx >= 0, idx * 3 + 5, torch.full_like(idx, -99))
+        sizes = [H.dist_rank_pixels(cols2, rows2, world, r, cr) for r in range(world)]
+        bufs = [torch.zeros(sizes[r], dtype=torch.int64) for r in range(world)] if rank == 0 else None
+        if rank == 0:
+            bufs[0] = mine
+            for r in range(1, world):
+                dist.recv(bufs[r], src=r)
+            frame = torch.full((rows2 * cols2,), -1, dtype=torch.int64)
+            for r in range(world):
+                ir = torch.from_numpy(H.dist_abs_pixels(cols2, rows2, world, r, cr)); ok = ir >= 0
+                frame[ir[ok]] = bufs[r][ok]
+            assert torch.equal(frame, torch.arange(rows2 * cols2, dtype=torch.int64) * 3 + 5), "library partition does not tile the frame"
+        else:
+            dist.send(mine, dst=0)
+    assert H.dist_photon_range(1003, world, rank) == D.photon_range(1003, world, rank)
+    i01 = [H.dist_photon_range(1003, world, r) for r in range(world)]
+    assert i01[0][0] == 0 and i01[-1][1] == 1003 and all(i01[r][1] == i01[r + 1][0] for r in range(world - 1))
+    if rank == 0:
+        print("LIBPART_OK")
     dist.barrier(); dist.destroy_process_group()
 """) % ROOT
 
@@ -54,4 +79,4 @@ def test_frame_gather_world2(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29541", str(w)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "GATHER_OK" in r.stdout and "PHOTONS_OK" in r.stdout
+    assert "GATHER_OK" in r.stdout and "PHOTONS_OK" in r.stdout and "LIBPART_OK" in r.stdout

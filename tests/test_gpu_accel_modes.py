@@ -95,7 +95,7 @@ def test_kernel_variants_give_identical_frames(drt, gpu_ctx_factory, name, spp, 
             assert getattr(res[7]["stats"], k) == getattr(other["stats"], k)
     assert res[7]["stats"].rays_deferred == 0
     if name == "gen_ortho_bunny":
-        assert auto["stats"].rays_deferred >= auto["stats"].rays_primary * 0.3
+        assert auto["stats"].rays_deferred > 1000        # every ray that reaches the mesh (the others miss its root box before any descent)
     if name == "p3_t11_sierp":          # the flat-scene kernel cannot enter an instance tree: every ray that reaches its root box is deferred
         assert res[0]["stats"].rays_deferred > 0
 
