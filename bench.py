@@ -70,13 +70,10 @@ def measured_peaks():
 
 
 def source_hash():
-    """Hash of the kernel sources + build flags: the instruction model in profiles/sass/ is valid for the build it was derived from."""
+    """Identity of the kernels' machine code (sha1 of the library's SASS, written by the build): the instruction model in profiles/sass/ is valid
+    for the build it was derived from."""
     from distraytracer_old_b200 import build as B
-    h = hashlib.sha1()
-    for f in sorted(os.listdir(B.CSRC)):
-        h.update(open(os.path.join(B.CSRC, f), "rb").read())
-    h.update(" ".join(B.NVCC_FLAGS).encode())
-    return h.hexdigest()[:16]
+    return B.kernel_hash()
 
 
 class ClockSampler:

@@ -30,6 +30,7 @@ def needs_build():
 
 def build(force=False, verbose=False, out=None, defines=()):
     if out is None and not force and not needs_build():
+        kernel_hash()
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out or LIB] + LINK_FLAGS
@@ -39,7 +40,27 @@ def build(force=False, verbose=False, out=None, defines=()):
         raise RuntimeError("nvcc failed building libdrt.so")
     if verbose:
         print(r.stderr)
+    if out is None:
+        kernel_hash(refresh=True)
     return out or LIB
+
+
+HASH_FILE = os.path.join(HERE, "libdrt.sass.sha1")
+
+
+def kernel_hash(refresh=False):
+    """sha1 of the SASS of every kernel in libdrt.so: the identity of the MACHINE CODE the instruction model in profiles/sass/ was derived
+    from (host-side edits do not change it; any change of a kernel does)."""
+    import hashlib
+    if not refresh and os.path.exists(HASH_FILE) and os.path.getmtime(HASH_FILE) >= os.path.getmtime(LIB):
+        return open(HASH_FILE).read().strip()
+    cuobjdump = os.path.join(os.path.dirname(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")), "cuobjdump")
+    r = subprocess.run([cuobjdump, "-sass", LIB], capture_output=True)
+    if r.returncode != 0:
+        return "unknown"
+    h = hashlib.sha1(r.stdout).hexdigest()[:16]
+    open(HASH_FILE, "w").write(h + "\n")
+    return h
 
 
 if __name__ == "__main__":

@@ -646,6 +646,7 @@ __device__ DRT_LEAN_INLINE int leanClosest32(const DScene& S, const FBvh& B, con
     return (stdBox ? te >= 0 : te > 0) ? __double2float_rd(te) : -1.0f;
   };
   while (true) {
+    // [sass:node-begin]  (tools/sass_model.py attributes the SASS between these markers to "one node visit")
     while (alive && ref >= 0) {
       const float4* q = reinterpret_cast<const float4*>(S.fnodes32 + ref);
       const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2); const int4 lk = __ldg(reinterpret_cast<const int4*>(q) + 3);
@@ -664,7 +665,9 @@ __device__ DRT_LEAN_INLINE int leanClosest32(const DScene& S, const FBvh& B, con
       else if (hr) ref = cr;
       else popNext();
     }
+    // [sass:node-end]
     if (!alive) break;
+    // [sass:leaf-begin]
     {
       const int code = ~ref, cnt = code & 7, first = code >> 3;
       for (int i = 0; i < cnt; ++i) {
@@ -672,6 +675,7 @@ __device__ DRT_LEAN_INLINE int leanClosest32(const DScene& S, const FBvh& B, con
         if (leanTri(S.tris + first + i, to.x, to.y, to.z, td.x, td.y, td.z, bestT, t, st, rank) && (t < bestT || rank < bestRank)) { bestT = t; bestTf = __double2float_ru(t); bestTri = first + i; bestRank = rank; bestSt = st; }
       }
     }
+    // [sass:leaf-end]
     popNext();
   }
   if (overflow) return -1;
@@ -695,6 +699,7 @@ __device__ DRT_LEAN_INLINE int leanShadow32(const DScene& S, const FBvh& B, cons
     return (stdBox ? tx >= 0 : tx > 0) && (dist - tx) > DRT_EPS;
   };
   while (true) {
+    // [sass:node-begin]  (tools/sass_model.py attributes the SASS between these markers to "one node visit")
     while (alive && ref >= 0) {
       const float4* q = reinterpret_cast<const float4*>(S.fnodes32 + ref);
       const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2); const int4 lk = __ldg(reinterpret_cast<const int4*>(q) + 3);
@@ -708,7 +713,9 @@ __device__ DRT_LEAN_INLINE int leanShadow32(const DScene& S, const FBvh& B, cons
       else if (sp > 0) ref = stkE[--sp];
       else alive = false;
     }
+    // [sass:node-end]
     if (!alive) break;
+    // [sass:leaf-begin]
     {
       const int code = ~ref, cnt = code & 7, first = code >> 3;
       for (int i = 0; i < cnt; ++i) {
@@ -716,6 +723,7 @@ __device__ DRT_LEAN_INLINE int leanShadow32(const DScene& S, const FBvh& B, cons
         if (leanTri(S.tris + first + i, to.x, to.y, to.z, td.x, td.y, td.z, DRT_DMAX, t, st, rank) && (dist - t) > DRT_EPS) { found = true; break; }
       }
     }
+    // [sass:leaf-end]
     if (found) break;
     if (sp > 0) ref = stkE[--sp]; else alive = false;
   }

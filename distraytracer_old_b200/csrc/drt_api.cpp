@@ -1,6 +1,7 @@
 // C ABI (include/drt.h) over the host interpreter/flattener and the device renderer.
 #include "../../include/drt.h"
 #include "renderer.h"
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -11,6 +12,9 @@ using namespace drt;
 
 namespace drt { double hostPhiloxU01(uint64_t seed, uint32_t stream, uint32_t a, uint32_t b, uint32_t c, uint32_t d); }
 
+typedef std::chrono::duration<double, std::milli> MsD;
+static double wallMs() { return MsD(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 struct drt_ctx {
   drt_config cfg;
   std::unique_ptr<HostScene> scene;
@@ -18,7 +22,7 @@ struct drt_ctx {
   std::string err, texDir, dataDir;
   drt_image_loader_fn loader = nullptr; void* loaderUser = nullptr;
   int spp = 0; long long photons = -1;
-  bool finalized = false;
+  bool finalized = false; double msUpload = 0;
   void freshScene() {
     scene.reset(new HostScene(cfg.cols, cfg.rows)); scene->setSeed(cfg.seed); finalized = false;
     if (!texDir.empty()) scene->setTexDir(texDir);
@@ -66,10 +70,14 @@ int drt_scene_finalize(drt_ctx* ctx, int32_t accel_mode) {
     if ((accel_mode & 3) == 3 || (accel_mode & ~(3 | 256 | 512)) != 0) throw std::runtime_error("unknown acceleration mode (use DRT_ACCEL_REFERENCE, DRT_ACCEL_REFERENCE_FAST or DRT_ACCEL_LBVH)");
     ctx->scene->overrideSpp(ctx->spp); ctx->scene->overridePhotons(ctx->photons);
     ctx->scene->finalize();
-    if (ctx->renderer) { ctx->renderer->setTraceMode(accel_mode); ctx->renderer->upload(*ctx->scene); ctx->finalized = true; } }, DRT_ERR_SCENE)
+    if (ctx->renderer) { ctx->renderer->setTraceMode(accel_mode); const double t0 = wallMs(); ctx->renderer->upload(*ctx->scene); ctx->msUpload = wallMs() - t0; ctx->finalized = true; } }, DRT_ERR_SCENE)
 }
 int drt_scene_reupload(drt_ctx* ctx) { NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized) throw std::runtime_error("scene not finalized"); ctx->renderer->upload(*ctx->scene, true); }, DRT_ERR_STATE) }
 int drt_accel_info(drt_ctx* ctx, double* out4) { NEED_DEV(ctx) GUARD(ctx, { if (!ctx->finalized || !out4) throw std::runtime_error("scene not finalized"); ctx->renderer->accelInfo(out4); }, DRT_ERR_STATE) }
+int drt_build_info(drt_ctx* ctx, double* o) {
+  GUARD(ctx, { if (!o) throw std::runtime_error("null output"); const HostScene& s = *ctx->scene;
+    o[0] = s.msParse; o[1] = s.msBvhOrder; o[2] = s.msBvhOrderDevice; o[3] = s.msBvhShape; o[4] = s.msFinalize; o[5] = (double)s.bvhDeviceBuilds; o[6] = (double)s.bvhObjects; o[7] = ctx->msUpload; }, DRT_ERR_SCENE)
+}
 int drt_scene_counts(drt_ctx* ctx, int64_t* o) {
   GUARD(ctx, { if (!o) throw std::runtime_error("null output"); ctx->scene->finalize(); const HostScene& s = *ctx->scene; std::memset(o, 0, 8 * sizeof(int64_t));
     o[0] = (int64_t)s.tris.size(); for (const FBvh& B : s.bvhs) if (B.fast) { ++o[1]; o[3] += B.triCount; } for (const FPrim& P : s.prims) if (P.pad0 >= 0) ++o[2];

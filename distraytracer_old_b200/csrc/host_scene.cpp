@@ -6,8 +6,11 @@
 #include <cstdlib>
 #include <fstream>
 #include <stdexcept>
+#include <chrono>
 
 namespace drt {
+static double nowMs() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 
 // ---------------------------------------------------------------------------------------------
 // tokens: PApplet.splitTokens(line, " ") + Java number parsing (missing token / bad number -> Missing)
@@ -306,33 +309,43 @@ int HostScene::buildList(const std::vector<HGeom>& objs, int listXform, const M4
   bmin = mn; bmax = mx; lists.push_back(L); return (int)lists.size() - 1;
 }
 
-// myBVH.addObjList (myGeomBase.java:360-386) over three centroid-sorted lists (:338-357); returns a child
-// reference (>= 0 inner node, < 0 ~list) and the node's box.  `en - st` is the reference's objListSize, which
-// at the root is one less than the number of objects actually present.
-int32_t HostScene::buildBvhNode(std::vector<HGeom> ls[3], int st, int en, int bvhXform, const M4& bvhM, V3& bmin, V3& bmax) {
-  int count = en - st;
-  if (count <= 5) {                                    // DistRayTracer.maxPrimsPerLeaf
-    int li = buildList(ls[0], bvhXform, bvhM, bmin, bmax);   // leaf keeps every object of the x-sorted list, in that order
-    return ~li;
+// Object order of the reference's median-split tree, from the centroid keys alone (myGeomBase.java:338-386, DistRayTracer.java:409-418).
+// A node receives its objects in the order its parent's split left them (the root: insertion order).  The reference keeps three lists per
+// node, list i = that order stable-sorted by centroid coordinate i (TreeMap<Double, List> groups equal keys in arrival order,
+// buildSortedObjAras); only two of them are ever read: the list of the split axis (first axis of strictly largest span, last - first of the
+// sorted list = max - min) which is cut at (int)(.5 * count), and list 0, whose order a leaf keeps.  So: an inner node stable-sorts its range
+// by the split-axis key and hands the two halves down; a leaf stable-sorts its range by x.  `count` is the reference's objListSize, which at
+// the root is one less than the m objects present: the last object of the root's split-axis order is dropped (it stays behind
+// at ord[count]); a root that is a leaf keeps all m.  keys = [3][n].
+static void refOrderRange(const double* keys, int n, int32_t* ord, int s, int m, int count) {
+  auto byAxis = [&](int ax) { const double* k = keys + (size_t)ax * n; std::stable_sort(ord + s, ord + s + m, [k](int32_t a, int32_t b) { return javaDoubleCompare(k[a], k[b]) < 0; }); };
+  if (count <= 5) { byAxis(0); return; }                // DistRayTracer.maxPrimsPerLeaf
+  double widest = -1; int axis = -1;
+  for (int i = 0; i < 3; ++i) {
+    const double* k = keys + (size_t)i * n; double lo = k[ord[s]], hi = lo;
+    for (int j = 1; j < m; ++j) { const double v = k[ord[s + j]]; if (javaDoubleCompare(v, lo) < 0) lo = v; if (javaDoubleCompare(v, hi) > 0) hi = v; }
+    const double span = hi - lo; if (widest < span) { widest = span; axis = i; }
   }
-  int split = (int)(.5 * count), n = (int)ls[0].size();
-  double widest = -1; int axis = -1;                   // DistRayTracer.java:409-418
-  for (int i = 0; i < 3; ++i) { double span = ls[i][n - 1].key[i] - ls[i][0].key[i]; if (widest < span) { widest = span; axis = i; } }
   if (axis < 0) throw std::runtime_error("BVH split axis undefined (NaN centroids)");
-  auto resort = [&](const std::vector<HGeom>& src, std::vector<HGeom> out[3]) {
-    for (int i = 0; i < 3; ++i) {
-      out[i] = src;
-      if (i != axis) std::stable_sort(out[i].begin(), out[i].end(), [i](const HGeom& a, const HGeom& b) { return javaDoubleCompare(a.key[i], b.key[i]) < 0; });
-    }
-  };
+  byAxis(axis);
+  const int split = (int)(.5 * count);
+  refOrderRange(keys, n, ord, s, split, split);
+  refOrderRange(keys, n, ord, s + split, count - split, count - split);
+}
+void HostScene::refOrderHost(int n, const double* keys, int32_t* ord) { for (int i = 0; i < n; ++i) ord[i] = i; if (n > 0) refOrderRange(keys, n, ord, 0, n, n - 1); }
+
+// myBVH.addObjList (myGeomBase.java:360-386) over the order computed above: the tree's SHAPE depends on the counts only.  Returns a child
+// reference (>= 0 inner node, < 0 ~list) and the node's box.
+int32_t HostScene::buildBvhNode(const std::vector<HGeom>& objs, const int32_t* ord, int s, int m, int count, int bvhXform, const M4& bvhM, V3& bmin, V3& bmax) {
+  if (count <= 5) {
+    std::vector<HGeom> leaf; leaf.reserve(m); for (int i = 0; i < m; ++i) leaf.push_back(objs[ord[s + i]]);
+    return ~buildList(leaf, bvhXform, bvhM, bmin, bmax);      // leaf keeps every object of the x-sorted list, in that order
+  }
+  const int split = (int)(.5 * count);
   int32_t me = (int32_t)nodes.size(); nodes.push_back(FNode()); std::memset(&nodes[me], 0, sizeof(FNode));
-  std::vector<HGeom> part(ls[axis].begin(), ls[axis].begin() + split), sub[3];
-  resort(part, sub);
   V3 lmn, lmx, rmn, rmx;
-  int32_t l = buildBvhNode(sub, st, st + split, bvhXform, bvhM, lmn, lmx);
-  std::vector<HGeom> part2(ls[axis].begin() + split, ls[axis].begin() + count), sub2[3];
-  resort(part2, sub2);
-  int32_t r = buildBvhNode(sub2, st + split, en, bvhXform, bvhM, rmn, rmx);
+  int32_t l = buildBvhNode(objs, ord, s, split, split, bvhXform, bvhM, lmn, lmx);
+  int32_t r = buildBvhNode(objs, ord, s + split, count - split, count - split, bvhXform, bvhM, rmn, rmx);
   FNode& nd = nodes[me];
   nd.left = l; nd.right = r;
   nd.lmin[0] = lmn.x; nd.lmin[1] = lmn.y; nd.lmin[2] = lmn.z; nd.lmax[0] = lmx.x; nd.lmax[1] = lmx.y; nd.lmax[2] = lmx.z;
@@ -350,11 +363,20 @@ void HostScene::endList(int type) {                                           //
   if (type == 0) { gm.kind = OK_LIST; gm.idx = buildList(tmpList_, gm.xform, M, gm.bmin, gm.bmax); }
   else {
     FBvh B; std::memset(&B, 0, sizeof(B)); B.xform = gm.xform; B.dropped = -1;
-    std::vector<HGeom> ls[3];
-    for (int i = 0; i < 3; ++i) { ls[i] = tmpList_; std::stable_sort(ls[i].begin(), ls[i].end(), [i](const HGeom& a, const HGeom& b) { return javaDoubleCompare(a.key[i], b.key[i]) < 0; }); }
     int first = (int)nodes.size();
     if (tmpList_.empty()) { V3 a, b; B.root = ~buildList(tmpList_, gm.xform, M, a, b); gm.bmin = a; gm.bmax = b; }
-    else B.root = buildBvhNode(ls, 0, (int)tmpList_.size() - 1, gm.xform, M, gm.bmin, gm.bmax);
+    else {
+      // the order is a function of the centroid keys alone: computed by the device (segmented radix sorts, csrc/refbvh.cuh) when the context has
+      // one and the list is large, else by the host recursion -- both give the same array, bit for bit (tests/test_gpu_refbvh.py)
+      const int n = (int)tmpList_.size(); std::vector<double> keys((size_t)3 * n); std::vector<int32_t> ord(n);
+      for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) keys[(size_t)k * n + i] = tmpList_[i].key[k];
+      bool done = false; const double t0 = nowMs();
+      if (orderer_ && n >= ordererMin_) { done = orderer_(n, keys.data(), ord.data()); if (done) ++bvhDeviceBuilds; }
+      if (!done) refOrderHost(n, keys.data(), ord.data());
+      const double t1 = nowMs(); msBvhOrder += t1 - t0; bvhObjects += n;
+      B.root = buildBvhNode(tmpList_, ord.data(), 0, n, n - 1, gm.xform, M, gm.bmin, gm.bmax);
+      msBvhShape += nowMs() - t1;
+    }
     B.nodeCount = (int)nodes.size() - first;
     B.bmin[0] = gm.bmin.x; B.bmin[1] = gm.bmin.y; B.bmin[2] = gm.bmin.z; B.bmax[0] = gm.bmax.x; B.bmax[1] = gm.bmax.y; B.bmax[2] = gm.bmax.z;
     gm.kind = OK_BVH; gm.idx = (int)bvhs.size(); bvhs.push_back(B);
@@ -413,7 +435,7 @@ void HostScene::addLight(int type, const Tokens& k) {                          /
 // ---------------------------------------------------------------------------------------------
 // interpreter (myRTFileReader.java:45-347)
 // ---------------------------------------------------------------------------------------------
-void HostScene::loadFile(const std::string& file, const std::string& dataDir) { dataDir_ = dataDir; if (texDir_.empty()) texDir_ = dataDir + "/txtrs_argb"; readFile(file, true); }
+void HostScene::loadFile(const std::string& file, const std::string& dataDir) { const double t0 = nowMs(); dataDir_ = dataDir; if (texDir_.empty()) texDir_ = dataDir + "/txtrs_argb"; readFile(file, true); msParse += nowMs() - t0; }
 void HostScene::readFile(const std::string& file, bool isMain) {
   std::ifstream in(dataDir_ + "/" + file);
   if (!in) { if (isMain) throw std::runtime_error("cannot read scene file " + dataDir_ + "/" + file); warnings.push_back("File Read Error : " + file); return; }
@@ -563,6 +585,7 @@ void HostScene::buildFastBvh(FBvh& B) {
 }
 
 void HostScene::finalize() {
+  const double tF0 = nowMs();
   tris.clear();
   for (FBvh& B : bvhs) buildFastBvh(B);
   top.clear();
@@ -589,6 +612,7 @@ void HostScene::finalize() {
       for (int k = 0; k < 3; ++k) { const double m = std::max(std::max(std::fabs(n.lmin[k]), std::fabs(n.lmax[k])), std::max(std::fabs(n.rmin[k]), std::fabs(n.rmax[k])));
         const float f = (float)m; B.absMax[k] = std::max(B.absMax[k], f >= m ? f : std::nextafter(f, INFINITY)); }
       if (n.left >= 0) st.push_back(n.left); if (n.right >= 0) st.push_back(n.right); } }
+  msFinalize = nowMs() - tF0;
 }
 
 void HostScene::dumpNode(int32_t ref, std::vector<int32_t>& out) const {

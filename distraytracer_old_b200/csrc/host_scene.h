@@ -24,6 +24,9 @@ struct HostImage { int w = 0, h = 0; std::vector<int32_t> px; };
 // returns false when the image cannot be provided
 typedef std::function<bool(const std::string& name, HostImage& out)> ImageLoader;
 
+// fills ord[n] with the object order of the reference's median-split tree (HostScene::refOrderHost); false = not done, the host does it
+typedef std::function<bool(int n, const double* keys, int32_t* ord)> BvhOrderer;
+
 class HostScene {
  public:
   HostScene(int cols, int rows);
@@ -35,6 +38,13 @@ class HostScene {
   void overrideSpp(int spp) { if (spp > 0) g.spp = spp; }
   void overridePhotons(long long n) { if (n >= 0) g.numPhotonsCast = (int)n; }
   void setSeed(uint64_t s) { g.seed = s; }
+  // object order of the reference's median-split tree from the [3][n] centroid keys (see host_scene.cpp); the device version is installed by
+  // the context when it owns a GPU and is used for lists of at least minObjects objects
+  static void refOrderHost(int n, const double* keys, int32_t* ord);
+  void setBvhOrderer(BvhOrderer o, int minObjects) { orderer_ = o; ordererMin_ = minObjects; }
+  int bvhDeviceBuilds = 0;              // BVHs whose order came from the device
+  double msBvhOrder = 0, msBvhOrderDevice = 0, msBvhShape = 0, msFinalize = 0, msParse = 0;   // host wall clock of the build phases (drt_build_info); msBvhOrderDevice = CUDA-event time inside the device orderer
+  long long bvhObjects = 0;             // objects handed to median-split builds
   // ---- flat result (valid after parsing; finalize() fills FGlobals counts)
   void finalize();
   FGlobals g;
@@ -92,7 +102,8 @@ class HostScene {
   void addGeom(const HGeom& gm, bool cmpIsLight);
   void endList(int type);
   int buildList(const std::vector<HGeom>& objs, int listXform, const M4& listM, V3& bmin, V3& bmax);
-  int32_t buildBvhNode(std::vector<HGeom> lists[3], int st, int en, int bvhXform, const M4& bvhM, V3& bmin, V3& bmax);
+  int32_t buildBvhNode(const std::vector<HGeom>& objs, const int32_t* ord, int s, int m, int count, int bvhXform, const M4& bvhM, V3& bmin, V3& bmax);
+  BvhOrderer orderer_; int ordererMin_ = 1 << 30;
   void addPrimitive(const Tokens& k);
   HGeom makePrim(int type, int flags, const std::vector<double>& data, V3 origin, V3 bmin, V3 bmax);
   void addInstance(const std::string& name, bool useShader);

@@ -70,6 +70,7 @@ def load_library():
         "drt_scene_info": (C.c_int, [vp, C.POINTER(i32)]),
         "drt_accel_info": (C.c_int, [vp, C.POINTER(dbl)]),
         "drt_scene_counts": (C.c_int, [vp, C.POINTER(i64)]),
+        "drt_build_info": (C.c_int, [vp, C.POINTER(dbl)]),
         "drt_emit_photons": (C.c_int, [vp, C.POINTER(Stats)]),
         "drt_render": (C.c_int, [vp, vp, C.POINTER(Stats)]),
         "drt_render_aov": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(Stats)]),
@@ -104,7 +105,7 @@ def load_library():
 
 EXPORTS = ["drt_create", "drt_destroy", "drt_last_error", "drt_set_image_loader", "drt_set_texture_dir", "drt_scene_reset",
            "drt_scene_command", "drt_scene_load_cli", "drt_scene_override", "drt_scene_finalize", "drt_scene_reupload",
-           "drt_scene_info", "drt_scene_counts", "drt_accel_info", "drt_emit_photons", "drt_render", "drt_render_aov", "drt_render_device", "drt_render_device_chunks", "drt_save_png",
+           "drt_scene_info", "drt_scene_counts", "drt_build_info", "drt_accel_info", "drt_emit_photons", "drt_render", "drt_render_aov", "drt_render_device", "drt_render_device_chunks", "drt_save_png",
            "drt_trace_rays", "drt_eval_texture", "drt_dump_bvh", "drt_obj_ctm", "drt_sample_u01", "drt_get_photons",
            "drt_emit_photons_range", "drt_photons_export_device", "drt_photons_build_device", "drt_photon_probe",
            "drt_comm_unique_id", "drt_comm_init", "drt_comm_destroy", "drt_render_distributed",
@@ -220,6 +221,11 @@ class Scene:
         o = (C.c_int64 * 8)()
         self.ctx._ck(self.L.drt_scene_counts(self.ctx.h, o))
         return {"tris_packed": o[0], "fast_bvhs": o[1], "top_tris_packed": o[2], "tris_in_fast_bvhs": o[3], "children": o[4], "pdata_doubles": o[5]}
+
+    def build_info(self):
+        o = (C.c_double * 8)()
+        self.ctx._ck(self.L.drt_build_info(self.ctx.h, o))
+        return {"parse_ms": o[0], "bvh_order_ms": o[1], "bvh_order_device_ms": o[2], "bvh_shape_ms": o[3], "finalize_ms": o[4], "bvh_device_builds": int(o[5]), "bvh_objects": int(o[6]), "upload_ms": o[7]}
 
     def accel_info(self):
         o = (C.c_double * 4)()

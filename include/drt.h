@@ -63,6 +63,10 @@ int drt_scene_override(drt_ctx* ctx, int32_t spp, int64_t photons); /* <=0 / <0 
 int drt_scene_finalize(drt_ctx* ctx, int32_t accel_mode);        /* flatten, build acceleration structures, upload to HBM */
 int drt_scene_reupload(drt_ctx* ctx);                            /* host->device copy of the flattened scene again (used by end-to-end timing) */
 int drt_accel_info(drt_ctx* ctx, double* out4);                  /* after finalize: GPU LBVH build ms, triangles and nodes it covers, scene bytes resident in HBM */
+/* host wall clock (ms) of the build phases of the current scene: [0] .cli interpretation (includes [1],[3]), [1] median-split object ordering
+   (myBVH.addObjList / buildSortedObjAras, myGeomBase.java:338-386) host or device, [2] the device part of [1] (CUDA events), [3] node / leaf-list
+   construction from the order, [4] finalize (packed triangles, FP32 node mirror), [5] BVHs ordered on the device, [6] objects ordered, [7] upload */
+int drt_build_info(drt_ctx* ctx, double* out8);
 int drt_scene_counts(drt_ctx* ctx, int64_t* out8);               /* flattener products of the fast paths: packed triangles, fast BVHs, packed top-level triangles, triangles in fast BVHs, children, pdata doubles, 0, 0 */
 int drt_scene_info(drt_ctx* ctx, int32_t* out16);                /* cols, rows, spp, top objects, lights, prims, instances, photon kind, shaders, nodes, xforms, lists, ... */
 
