@@ -605,8 +605,8 @@ __device__ DRT_LEAN_INLINE int leanShadow(const DScene& S, const FBvh& B, const 
 // comfortable float range get M = +inf: every comparison fails and every box takes the exact test.  Entry times only order and prune
 // (conservative lower bound near32 - M), exactly as in the FP64 descent; triangles are always tested in FP64.
 struct Lean32 { float ix, iy, iz, ox, oy, oz, M, M2; };
-__device__ __forceinline__ Lean32 makeLean32(const FBvh& B, double ox, double oy, double oz, double ax, double ay, double az) {
-  const double ix = 1.0 / ax, iy = 1.0 / ay, iz = 1.0 / az; Lean32 L;
+__device__ __forceinline__ Lean32 makeLean32(const FBvh& B, double ox, double oy, double oz, const D3& inv) {      // inv = rayInv() of the ray the boxes are tested with
+  const double ix = inv.x, iy = inv.y, iz = inv.z; Lean32 L;
   L.ix = (float)ix; L.iy = (float)iy; L.iz = (float)iz; L.ox = (float)(ox * ix); L.oy = (float)(oy * iy); L.oz = (float)(oz * iz);
   const double ex = (3.0 * B.absMax[0] + 2.0 * fabs(ox)) * fabs(ix), ey = (3.0 * B.absMax[1] + 2.0 * fabs(oy)) * fabs(iy), ez = (3.0 * B.absMax[2] + 2.0 * fabs(oz)) * fabs(iz);
   double m = ex > ey ? ex : ey; m = ez > m ? ez : m;
@@ -632,8 +632,8 @@ __device__ __noinline__ double boxStdEntry(const double* __restrict__ box6, doub
   double te; return leanBoxStd(__ldg(box6), __ldg(box6 + 1), __ldg(box6 + 2), __ldg(box6 + 3), __ldg(box6 + 4), __ldg(box6 + 5), R, te) > 0 ? te : -1.0;
 }
 template <int CAP>
-__device__ DRT_LEAN_INLINE int leanClosest32(const DScene& S, const FBvh& B, const D3 bo, const D3 ba, const D3 to, const D3 td, const D3 rawDir, Hit& out) {
-  const Lean32 L = makeLean32(B, bo.x, bo.y, bo.z, ba.x, ba.y, ba.z);
+__device__ DRT_LEAN_INLINE int leanClosest32(const DScene& S, const FBvh& B, const D3 bo, const D3 ba, const D3 binv, const D3 to, const D3 td, const D3 rawDir, Hit& out) {
+  const Lean32 L = makeLean32(B, bo.x, bo.y, bo.z, binv);
   const bool stdBox = S.accelMode == 2;
   uint2 stkE[CAP]; int sp = 0; bool overflow = false;
   double bestT = DRT_DMAX; float bestTf = __int_as_float(0x7f800000);        // bestTf = bestT rounded UP: te_lb >= bestTf implies te >= bestT
@@ -684,8 +684,8 @@ __device__ DRT_LEAN_INLINE int leanClosest32(const DScene& S, const FBvh& B, con
   out.loc = d3((td.x * bestT) + to.x, (td.y * bestT) + to.y, (td.z * bestT) + to.z); out.rawDir = rawDir; return 1;
 }
 template <int CAP>
-__device__ DRT_LEAN_INLINE int leanShadow32(const DScene& S, const FBvh& B, const D3 bo, const D3 ba, const D3 to, const D3 td, double dist) {
-  const Lean32 L = makeLean32(B, bo.x, bo.y, bo.z, ba.x, ba.y, ba.z);
+__device__ DRT_LEAN_INLINE int leanShadow32(const DScene& S, const FBvh& B, const D3 bo, const D3 ba, const D3 binv, const D3 to, const D3 td, double dist) {
+  const Lean32 L = makeLean32(B, bo.x, bo.y, bo.z, binv);
   const bool stdBox = S.accelMode == 2;
   // (dist - entry) > eps decided on near32 when it clears the bound: entry < dist - eps - M  /  entry > dist - eps + M
   const float accBelow = __double2float_rd((dist - DRT_EPS) - (double)L.M * 1.000001), rejAbove = __double2float_ru((dist - DRT_EPS) + (double)L.M * 1.000001);
@@ -743,14 +743,14 @@ struct Frame { int32_t node; double tL; };     // node >= 0: "after left" of tha
 // closest hit.  Every function returns 1 (hit), 0 (miss) or -1 (this kernel variant cannot serve the ray: defer it)
 // ---------------------------------------------------------------------------------------------------------------
 template <int F, int LVL>
-__device__ __forceinline__ int accelClosestImpl(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc);
+__device__ __forceinline__ int accelClosestImpl(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, int transXf, double time, Hit& out, TraceCounters* tc);
 // the generic variant keeps one outlined copy per level (code size); the lean variants inline everything so that ray / hit records stay in registers
 template <int F, int LVL>
-__device__ __noinline__ int accelClosestOut(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc) { return accelClosestImpl<F, LVL>(S, kind, idx, _ray, trans, time, out, tc); }
+__device__ __noinline__ int accelClosestOut(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, int transXf, double time, Hit& out, TraceCounters* tc) { return accelClosestImpl<F, LVL>(S, kind, idx, _ray, trans, transXf, time, out, tc); }
 template <int F, int LVL>
-__device__ __forceinline__ int accelClosest(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc) {
-  if constexpr (F == TF_ALL) return accelClosestOut<F, LVL>(S, kind, idx, _ray, trans, time, out, tc);
-  else return accelClosestImpl<F, LVL>(S, kind, idx, _ray, trans, time, out, tc);
+__device__ __forceinline__ int accelClosest(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, int transXf, double time, Hit& out, TraceCounters* tc) {
+  if constexpr (F == TF_ALL) return accelClosestOut<F, LVL>(S, kind, idx, _ray, trans, transXf, time, out, tc);
+  else return accelClosestImpl<F, LVL>(S, kind, idx, _ray, trans, transXf, time, out, tc);
 }
 
 // myGeomList.traverseStruct: every child gets a fresh transform of `_ray`; first strictly smaller t wins;
@@ -780,7 +780,7 @@ __device__ __forceinline__ double leafClosest(const DScene& S, int listIdx, Ray&
         if constexpr (!(F & TF_LITERAL1)) { defer = true; return clsT; }
         else {
           Hit h; hitReset(h);
-          const int got = accelClosest<F, 2>(S, I.baseKind, I.baseIdx, r, r, time, h, tc);
+          const int got = accelClosest<F, 2>(S, I.baseKind, I.baseIdx, r, r, -1, time, h, tc);
           if (got < 0) { defer = true; return clsT; }
           if (got && h.t < clsT) {
             clsT = h.t; res.t = h.t; res.prim = h.prim; res.arg0 = h.arg0; res.arg1 = h.arg1; res.state = h.state; res.loc = h.loc; res.rawDir = h.rawDir;
@@ -799,7 +799,7 @@ __device__ __forceinline__ double leafClosest(const DScene& S, int listIdx, Ray&
 // combines with "min, left wins ties", the overall winner is the DFS-first minimum over all visited leaves; the
 // per-subtree minima needed for the pruning decisions live on an explicit frame stack.
 template <int F, int LVL>
-__device__ __forceinline__ int accelClosestImpl(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, Hit& out, TraceCounters* tc) {
+__device__ __forceinline__ int accelClosestImpl(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, int transXf, double time, Hit& out, TraceCounters* tc) {
   constexpr bool LITERAL = (LVL == 1) ? ((F & TF_LITERAL1) != 0) : ((F & TF_LEVEL2) != 0);      // literal recursion compiled in at this level?
   constexpr bool NONLEAN = (LVL == 1) ? ((F & TF_NONLEAN) != 0) : ((F & TF_LEVEL2) != 0);
   const D3 inv = rayInv(trans);
@@ -818,8 +818,11 @@ __device__ __forceinline__ int accelClosestImpl(const DScene& S, int kind, int i
   if (S.accelMode != 0 && B.fast != 0) {
     const double len2 = _ray.norm ? 1.0 : dot3(_ray.d, _ray.d);
     if (fastUsable(S, B, len2)) {
-      const Ray r = xfRay(_ray, S.xforms[B.triXform].inv);          // what every leaf child of this mesh would be tested with
-      const bool one = sameRay(trans, r);
+      // what every leaf child of this mesh would be tested with.  getTransformedRay is a pure function of (ray, CTM) once the source direction is
+      // unit length, so when `trans` was formed from this very ray with the triangles' own CTM the two rays are the same bits: nothing to recompute
+      const bool sameXf = _ray.norm && transXf == B.triXform;
+      const Ray r = sameXf ? trans : xfRay(_ray, S.xforms[B.triXform].inv);
+      const bool one = sameXf || sameRay(trans, r);
 #if DRT_LEAN
       if (regularDir(trans.a)) {
         // one instantiation per lean kernel (one traversal stack in its frame): flat scenes test boxes and triangles with the same ray, scenes
@@ -830,8 +833,8 @@ __device__ __forceinline__ int accelClosestImpl(const DScene& S, int kind, int i
           return got;
         } else {
 #if DRT_LEAN32
-          if constexpr ((F & TF_LITERAL1) != 0) return leanClosest32<DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out);
-          else { if (!one) return -1; return leanClosest32<DRT_LSTACK>(S, B, trans.o, trans.a, trans.o, trans.a, _ray.d, out); }      // flat scenes: one ray, one register set
+          if constexpr ((F & TF_LITERAL1) != 0) return leanClosest32<DRT_LSTACK>(S, B, trans.o, trans.a, inv, r.o, r.d, _ray.d, out);
+          else { if (!one) return -1; return leanClosest32<DRT_LSTACK>(S, B, trans.o, trans.a, inv, trans.o, trans.a, _ray.d, out); }      // flat scenes: one ray, one register set
 #else
           if constexpr ((F & TF_LITERAL1) != 0) return leanClosest<false, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc);
           else { if (!one) return -1; return leanClosest<true, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, _ray.d, out, tc); }
@@ -911,8 +914,8 @@ __device__ __forceinline__ int closestHitT(const DScene& S, Ray& ray, double tim
           if (primTest(S, I.baseIdx, tr, time, ph) && ph.t < best.t) { takeHit(S, best, ph, I.baseIdx, tr, tr.d, o.xform); if (shader >= 0) best.shaderOverride = shader; best.inst = serial; }
           continue;
         }
-        got = accelClosest<F, 1>(S, I.baseKind, I.baseIdx, tr, tr, time, h, tc);
-      } else got = accelClosest<F, 1>(S, o.kind, o.idx, ray, tr, time, h, tc);
+        got = accelClosest<F, 1>(S, I.baseKind, I.baseIdx, tr, tr, -1, time, h, tc);
+      } else got = accelClosest<F, 1>(S, o.kind, o.idx, ray, tr, o.xform, time, h, tc);
       if (got < 0) return -1;
       if (got && h.t < best.t) {
         best.t = h.t; best.prim = h.prim; best.arg0 = h.arg0; best.arg1 = h.arg1; best.state = h.state; best.hitXform = h.hitXform; best.loc = h.loc; best.rawDir = h.rawDir;
@@ -929,13 +932,13 @@ __device__ __forceinline__ bool closestHit(const DScene& S, Ray& ray, double tim
 // (top-level or BVH leaf) gates on its own box with the same rule.  1 / 0 / -1 as above.
 // ---------------------------------------------------------------------------------------------------------------
 template <int F, int LVL>
-__device__ __forceinline__ int accelShadowImpl(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc);
+__device__ __forceinline__ int accelShadowImpl(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, int transXf, double time, double dist, TraceCounters* tc);
 template <int F, int LVL>
-__device__ __noinline__ int accelShadowOut(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc) { return accelShadowImpl<F, LVL>(S, kind, idx, _ray, trans, time, dist, tc); }
+__device__ __noinline__ int accelShadowOut(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, int transXf, double time, double dist, TraceCounters* tc) { return accelShadowImpl<F, LVL>(S, kind, idx, _ray, trans, transXf, time, dist, tc); }
 template <int F, int LVL>
-__device__ __forceinline__ int accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc) {
-  if constexpr (F == TF_ALL) return accelShadowOut<F, LVL>(S, kind, idx, _ray, trans, time, dist, tc);
-  else return accelShadowImpl<F, LVL>(S, kind, idx, _ray, trans, time, dist, tc);
+__device__ __forceinline__ int accelShadow(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, int transXf, double time, double dist, TraceCounters* tc) {
+  if constexpr (F == TF_ALL) return accelShadowOut<F, LVL>(S, kind, idx, _ray, trans, transXf, time, dist, tc);
+  else return accelShadowImpl<F, LVL>(S, kind, idx, _ray, trans, transXf, time, dist, tc);
 }
 
 template <int F, int LVL>
@@ -953,14 +956,14 @@ __device__ __forceinline__ int listShadow(const DScene& S, int listIdx, Ray& _ra
       if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, I.baseIdx, r, time, h) && (dist - h.t) > DRT_EPS) return 1; }
       else if constexpr (LVL == 1) {
         if constexpr (!(F & TF_LITERAL1)) return -1;
-        else { const int got = accelShadow<F, 2>(S, I.baseKind, I.baseIdx, r, r, time, dist, tc); if (got != 0) return got; }
+        else { const int got = accelShadow<F, 2>(S, I.baseKind, I.baseIdx, r, r, -1, time, dist, tc); if (got != 0) return got; }
       }
     }
   }
   return 0;
 }
 template <int F, int LVL>
-__device__ __forceinline__ int accelShadowImpl(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, double time, double dist, TraceCounters* tc) {
+__device__ __forceinline__ int accelShadowImpl(const DScene& S, int kind, int idx, Ray& _ray, const Ray& trans, int transXf, double time, double dist, TraceCounters* tc) {
   constexpr bool LITERAL = (LVL == 1) ? ((F & TF_LITERAL1) != 0) : ((F & TF_LEVEL2) != 0);
   constexpr bool NONLEAN = (LVL == 1) ? ((F & TF_NONLEAN) != 0) : ((F & TF_LEVEL2) != 0);
   const D3 inv = rayInv(trans);
@@ -968,8 +971,9 @@ __device__ __forceinline__ int accelShadowImpl(const DScene& S, int kind, int id
   if (kind == OK_LIST) return listShadow<F, LVL>(S, idx, _ray, trans, inv, time, dist, tc, xc);
   const FBvh& B = S.bvhs[idx];
   if (S.accelMode != 0 && B.fast != 0) {                              // any-hit does not depend on the visiting order
-    const Ray r = xfRay(_ray, S.xforms[B.triXform].inv);
-    const bool one = sameRay(trans, r);
+    const bool sameXf = _ray.norm && transXf == B.triXform;          // see accelClosestImpl
+    const Ray r = sameXf ? trans : xfRay(_ray, S.xforms[B.triXform].inv);
+    const bool one = sameXf || sameRay(trans, r);
 #if DRT_LEAN
     if (regularDir(trans.a)) {
       if constexpr (F == TF_ALL) {
@@ -978,8 +982,8 @@ __device__ __forceinline__ int accelShadowImpl(const DScene& S, int kind, int id
         return got;
       } else {
 #if DRT_LEAN32
-        if constexpr ((F & TF_LITERAL1) != 0) return leanShadow32<DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, dist);
-        else { if (!one) return -1; return leanShadow32<DRT_LSTACK>(S, B, trans.o, trans.a, trans.o, trans.a, dist); }
+        if constexpr ((F & TF_LITERAL1) != 0) return leanShadow32<DRT_LSTACK>(S, B, trans.o, trans.a, inv, r.o, r.d, dist);
+        else { if (!one) return -1; return leanShadow32<DRT_LSTACK>(S, B, trans.o, trans.a, inv, trans.o, trans.a, dist); }
 #else
         if constexpr ((F & TF_LITERAL1) != 0) return leanShadow<false, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, dist, tc);
         else { if (!one) return -1; return leanShadow<true, DRT_LSTACK>(S, B, trans.o, trans.a, r.o, r.d, dist, tc); }
@@ -1024,8 +1028,8 @@ __device__ __forceinline__ int anyHitT(const DScene& S, Ray& ray, double time, d
     else if (o.kind == OK_INSTANCE) {
       const FInstance I = S.instances[o.idx];
       if (I.baseKind == OK_PRIM) { if (tc) ++tc->prim; if (primTest(S, I.baseIdx, tr, time, h) && (dist - h.t) > DRT_EPS) return 1; }
-      else { const int got = accelShadow<F, 1>(S, I.baseKind, I.baseIdx, tr, tr, time, dist, tc); if (got != 0) return got; }
-    } else { const int got = accelShadow<F, 1>(S, o.kind, o.idx, ray, tr, time, dist, tc); if (got != 0) return got; }
+      else { const int got = accelShadow<F, 1>(S, I.baseKind, I.baseIdx, tr, tr, -1, time, dist, tc); if (got != 0) return got; }
+    } else { const int got = accelShadow<F, 1>(S, o.kind, o.idx, ray, tr, o.xform, time, dist, tc); if (got != 0) return got; }
   }
   return 0;
 }

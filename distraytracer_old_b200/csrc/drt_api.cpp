@@ -3,6 +3,7 @@
 #include "renderer.h"
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -26,6 +27,10 @@ struct drt_ctx {
   void freshScene() {
     scene.reset(new HostScene(cfg.cols, cfg.rows)); scene->setSeed(cfg.seed); finalized = false;
     if (!texDir.empty()) scene->setTexDir(texDir);
+    if (renderer) {     // median-split BVHs over large object lists are ordered on the device (csrc/refbvh.cuh); DRT_REFBVH_MIN=<objects> moves the threshold
+      Renderer* r = renderer.get(); HostScene* sc = scene.get(); const char* e = getenv("DRT_REFBVH_MIN");
+      scene->setBvhOrderer([r, sc](int n, const double* keys, int32_t* ord) { double ms = 0; const bool ok = r->orderBvh(n, keys, ord, &ms); sc->msBvhOrderDevice += ms; return ok; }, e ? atoi(e) : 4096);
+    }
     if (loader) { drt_image_loader_fn fn = loader; void* u = loaderUser;
       scene->setImageLoader([fn, u](const std::string& name, HostImage& out) { int32_t w = 0, h = 0; const int32_t* px = nullptr; if (fn(u, name.c_str(), &w, &h, &px) != 0 || !px) return false; out.w = w; out.h = h; out.px.assign(px, px + (size_t)w * h); return true; }); }
   }
@@ -77,6 +82,12 @@ int drt_accel_info(drt_ctx* ctx, double* out4) { NEED_DEV(ctx) GUARD(ctx, { if (
 int drt_build_info(drt_ctx* ctx, double* o) {
   GUARD(ctx, { if (!o) throw std::runtime_error("null output"); const HostScene& s = *ctx->scene;
     o[0] = s.msParse; o[1] = s.msBvhOrder; o[2] = s.msBvhOrderDevice; o[3] = s.msBvhShape; o[4] = s.msFinalize; o[5] = (double)s.bvhDeviceBuilds; o[6] = (double)s.bvhObjects; o[7] = ctx->msUpload; }, DRT_ERR_SCENE)
+}
+int drt_bvh_order(drt_ctx* ctx, int32_t n, const double* keys, int32_t* ord, int32_t on_device) {
+  if (on_device) { NEED_DEV(ctx) }
+  GUARD(ctx, { if (n < 0 || (n > 0 && (!keys || !ord))) throw std::runtime_error("bad order buffers");
+    if (!on_device) HostScene::refOrderHost(n, keys, ord);
+    else { double ms = 0; if (!ctx->renderer->orderBvh(n, keys, ord, &ms)) throw std::runtime_error("the device declined this key set (fewer than 2 objects, NaN keys or undefined spans)"); } }, DRT_ERR_SCENE)
 }
 int drt_scene_counts(drt_ctx* ctx, int64_t* o) {
   GUARD(ctx, { if (!o) throw std::runtime_error("null output"); ctx->scene->finalize(); const HostScene& s = *ctx->scene; std::memset(o, 0, 8 * sizeof(int64_t));

@@ -419,6 +419,7 @@ __global__ void k_eval_texture(const __grid_constant__ DScene S, int shader, lon
 
 #include "photon.cuh"
 #include "lbvh.cuh"
+#include "refbvh.cuh"
 
 namespace drt {
 
@@ -457,7 +458,7 @@ struct SceneArena {
 };
 
 struct Renderer::Impl {
-  DScene ds; SceneArena arena; DBuf<FNode> lbvhNodeBuf; DBuf<FNode32> lbvhNode32Buf; DBuf<FTri> lbvhTriBuf; LbvhScratch lbvhScratch;
+  DScene ds; SceneArena arena; DBuf<FNode> lbvhNodeBuf; DBuf<FNode32> lbvhNode32Buf; DBuf<FTri> lbvhTriBuf; LbvhScratch lbvhScratch; RefBvhScratch refScratch;
   DBuf<RayRec> rays[2]; DBuf<Hit> hits; DBuf<Hit> hits0; DBuf<SurfRec> surf; DBuf<NodeRec> nodes; Counters* ctr = nullptr; Counters* ctrHost = nullptr;
   DBuf<uint32_t> deferT, deferL;                 // deferral lists of the lean trace / light kernels (ray indices of one level)
   std::vector<cudaEvent_t> evPool;               // stage timing of a whole frame without a host sync per level
@@ -490,7 +491,7 @@ Renderer::Renderer(int device) : impl_(new Impl), device_(device) {
 }
 Renderer::~Renderer() {
   cudaSetDevice(device_);
-  impl_->arena.release(); impl_->lbvhNodeBuf.release(); impl_->lbvhNode32Buf.release(); impl_->lbvhTriBuf.release(); impl_->lbvhScratch.release();
+  impl_->arena.release(); impl_->lbvhNodeBuf.release(); impl_->lbvhNode32Buf.release(); impl_->lbvhTriBuf.release(); impl_->lbvhScratch.release(); impl_->refScratch.release();
   impl_->rays[0].release(); impl_->rays[1].release(); impl_->hits.release(); impl_->hits0.release(); impl_->surf.release(); impl_->nodes.release();
   impl_->oArgb.release(); impl_->oPrim.release(); impl_->oInst.release(); impl_->oRgb.release(); impl_->oT.release();
   impl_->deferT.release(); impl_->deferL.release(); for (auto& e : impl_->evPool) cudaEventDestroy(e);
@@ -498,6 +499,12 @@ Renderer::~Renderer() {
   cudaFree(impl_->ctr); cudaFreeHost(impl_->ctrHost);
   for (auto& e : impl_->ev) cudaEventDestroy(e);
   cudaStreamDestroy((cudaStream_t)stream_); delete impl_;
+}
+
+// object order of the reference-topology median-split tree on the device (refbvh.cuh); false = the host recursion has to do it
+bool Renderer::orderBvh(int n, const double* keys, int32_t* ord, double* ms) {
+  CK(cudaSetDevice(device_));
+  return refOrderDevice(n, keys, ord, impl_->refScratch, (cudaStream_t)stream_, ms);
 }
 
 void Renderer::upload(const HostScene& hs, bool sameScene) {

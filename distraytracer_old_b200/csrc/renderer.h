@@ -24,6 +24,7 @@ class Renderer {
   Renderer(int device);
   ~Renderer();
   void upload(const HostScene& hs, bool sameScene = false);   // flat scene -> HBM (sameScene: a re-upload of what is already resident, keeps the depth hint)
+  bool orderBvh(int n, const double* keys3n, int32_t* ord, double* msDevice);   // device twin of HostScene::refOrderHost (csrc/refbvh.cuh)
   void setBatchRays(long long n) { batchRays_ = n; }
   void setCounters(bool on) { counters_ = on; }
   void setTraceMode(int m) { traceMode_ = m; }

@@ -71,6 +71,7 @@ def load_library():
         "drt_accel_info": (C.c_int, [vp, C.POINTER(dbl)]),
         "drt_scene_counts": (C.c_int, [vp, C.POINTER(i64)]),
         "drt_build_info": (C.c_int, [vp, C.POINTER(dbl)]),
+        "drt_bvh_order": (C.c_int, [vp, i32, vp, vp, i32]),
         "drt_emit_photons": (C.c_int, [vp, C.POINTER(Stats)]),
         "drt_render": (C.c_int, [vp, vp, C.POINTER(Stats)]),
         "drt_render_aov": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(Stats)]),
@@ -105,7 +106,7 @@ def load_library():
 
 EXPORTS = ["drt_create", "drt_destroy", "drt_last_error", "drt_set_image_loader", "drt_set_texture_dir", "drt_scene_reset",
            "drt_scene_command", "drt_scene_load_cli", "drt_scene_override", "drt_scene_finalize", "drt_scene_reupload",
-           "drt_scene_info", "drt_scene_counts", "drt_build_info", "drt_accel_info", "drt_emit_photons", "drt_render", "drt_render_aov", "drt_render_device", "drt_render_device_chunks", "drt_save_png",
+           "drt_scene_info", "drt_scene_counts", "drt_build_info", "drt_bvh_order", "drt_accel_info", "drt_emit_photons", "drt_render", "drt_render_aov", "drt_render_device", "drt_render_device_chunks", "drt_save_png",
            "drt_trace_rays", "drt_eval_texture", "drt_dump_bvh", "drt_obj_ctm", "drt_sample_u01", "drt_get_photons",
            "drt_emit_photons_range", "drt_photons_export_device", "drt_photons_build_device", "drt_photon_probe",
            "drt_comm_unique_id", "drt_comm_init", "drt_comm_destroy", "drt_render_distributed",
@@ -166,6 +167,14 @@ class Context:
         buf = (C.c_uint8 * 128).from_buffer_copy(id128) if id128 is not None else None
         self._ck(self.L.drt_comm_init(self.h, buf, world, rank))
         self.world, self.rank = world, rank
+
+    def bvh_order(self, keys, on_device):
+        """Parity probe: object order of the reference's median-split BVH for centroid keys [n, 3] (host recursion or device builder)."""
+        k = np.ascontiguousarray(np.asarray(keys, dtype=np.float64).T)          # [3][n]
+        n = k.shape[1]
+        ord_ = np.empty(n, dtype=np.int32)
+        self._ck(self.L.drt_bvh_order(self.h, n, k.ctypes.data, ord_.ctypes.data, 1 if on_device else 0))
+        return ord_
 
     def close(self):
         if getattr(self, "h", None):

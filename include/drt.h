@@ -67,6 +67,10 @@ int drt_accel_info(drt_ctx* ctx, double* out4);                  /* after finali
    (myBVH.addObjList / buildSortedObjAras, myGeomBase.java:338-386) host or device, [2] the device part of [1] (CUDA events), [3] node / leaf-list
    construction from the order, [4] finalize (packed triangles, FP32 node mirror), [5] BVHs ordered on the device, [6] objects ordered, [7] upload */
 int drt_build_info(drt_ctx* ctx, double* out8);
+/* parity probe: object order of the reference's median-split BVH (myBVH.addObjList, myGeomBase.java:338-386) over n objects with centroid keys
+   keys3n = [3][n]; ord[n] = leaves left to right, each in the order the reference's leaf list holds them, the object dropped at the root
+    last.  on_device != 0: the device builder (segmented radix sorts), else the host recursion -- the two must agree bit for bit. */
+int drt_bvh_order(drt_ctx* ctx, int32_t n, const double* keys3n, int32_t* ord, int32_t on_device);
 int drt_scene_counts(drt_ctx* ctx, int64_t* out8);               /* flattener products of the fast paths: packed triangles, fast BVHs, packed top-level triangles, triangles in fast BVHs, children, pdata doubles, 0, 0 */
 int drt_scene_info(drt_ctx* ctx, int32_t* out16);                /* cols, rows, spp, top objects, lights, prims, instances, photon kind, shaders, nodes, xforms, lists, ... */
 
