@@ -76,7 +76,8 @@ struct DScene {
   // fast-BVH view: packed triangles and the node array their fastRoot indexes (== nodes, or the GPU-built LBVH nodes); accelMode = drt.h DRT_ACCEL_*
   const FTri* tris; const FNode* fnodes; const FNode32* fnodes32; int32_t accelMode; int32_t padA;
   // photon map (hash grid), see photon kernels
-  const double* phPos; const double* phPwr; const uint32_t* cellStart; const uint32_t* cellEnd; uint32_t gridDim[3]; uint32_t numPhotons; double gridMin[3]; double cellSize;
+  const double* phPos; const double* phPwr; const uint32_t* cellStart; const float* phPos32; uint32_t gridDim[3]; uint32_t numPhotons; double gridMin[3]; double cellSize;
+  float phAbsMax; float padP;      // phPos32: float4 mirror of phPos (pre-test of the gather); phAbsMax: largest |coordinate| of a stored photon, rounded up
   FGlobals g;
 };
 

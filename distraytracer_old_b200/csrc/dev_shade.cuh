@@ -27,6 +27,13 @@ __device__ inline D3 primNormal(const DScene& S, const FPrim& P, D3 pt, int arg0
     case PT_PLANE: return norm3(d3(q[4 * state], q[4 * state + 1], q[4 * state + 2]));
     case PT_HCYL: n = (arg0 == 1) ? d3((q[0] - pt.x), 0, (q[2] - pt.z)) : d3((pt.x - q[0]), 0, (pt.z - q[2])); n = norm3(n); if (P.flags & PF_INVERTED) n = scale3(n, -1); return n;
     case PT_CYL: if (arg0 >= 2) n = d3((pt.x - q[0]), 0, (pt.z - q[2])); else n = d3(q[7 + 4 * arg0], q[8 + 4 * arg0], q[9 + 4 * arg0]); n = norm3(n); if (P.flags & PF_INVERTED) n = scale3(n, -1); return n;
+    case PT_QUADRIC: {        // gradient; the far root (arg0 = 1) is seen from inside: flipped like the inside of a hollow cylinder
+      n = d3((((2 * q[0]) * pt.x) + (q[3] * pt.y)) + ((q[4] * pt.z) + q[6]), (((2 * q[1]) * pt.y) + (q[3] * pt.x)) + ((q[5] * pt.z) + q[7]), (((2 * q[2]) * pt.z) + (q[4] * pt.x)) + ((q[5] * pt.y) + q[8]));
+      n = norm3(n); if (arg0 == 1) n = scale3(n, -1); if (P.flags & PF_INVERTED) n = scale3(n, -1); return n; }
+    case PT_TORUS: {
+      const double x = pt.x - q[0], y = pt.y - q[1], z = pt.z - q[2], m = sqrt((x * x) + (z * z));
+      n = (m > 0) ? d3(x - ((q[3] * x) / m), y, z - ((q[3] * z) / m)) : d3(0, y, 0);
+      n = norm3(n); if (P.flags & PF_INVERTED) n = scale3(n, -1); return n; }
     case PT_BOX: switch (arg1) { case 0: return d3(-1, 0, 0); case 1: return d3(0, -1, 0); case 2: return d3(0, 0, -1); case 3: return d3(1, 0, 0); case 4: return d3(0, 1, 0); case 5: return d3(0, 0, 1); default: return d3(0, 0, -1); }
   }
   return d3(0, 0, 1);

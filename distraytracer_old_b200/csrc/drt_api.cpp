@@ -89,6 +89,26 @@ int drt_bvh_order(drt_ctx* ctx, int32_t n, const double* keys, int32_t* ord, int
     if (!on_device) HostScene::refOrderHost(n, keys, ord);
     else { double ms = 0; if (!ctx->renderer->orderBvh(n, keys, ord, &ms)) throw std::runtime_error("the device declined this key set (fewer than 2 objects, NaN keys or undefined spans)"); } }, DRT_ERR_SCENE)
 }
+int64_t drt_lbvh_probe(drt_ctx* ctx, int32_t fast_index, int32_t which, double* box6, double* verts9, int32_t* prim_serial, int32_t* links2, double* boxes12, int64_t cap_tris) {
+  if (!ctx) return DRT_ERR_BAD_ARG; if (which) { NEED_DEV(ctx) }
+  try {
+    if (!ctx->finalized && which) throw std::runtime_error("scene not finalized");
+    ctx->scene->finalize(); const HostScene& hs = *ctx->scene; std::vector<FTri> tris; std::vector<FNode> nodes; int32_t info[4] = {0, 0, 0, 0}; long long n = -1; int k = 0;
+    for (const FBvh& B : hs.bvhs) if (B.fast && k++ == fast_index) {
+      if (box6) { for (int i = 0; i < 3; ++i) { box6[i] = B.bmin[i]; box6[3 + i] = B.bmax[i]; } }
+      if (!which) { tris.assign(hs.tris.begin() + B.triStart, hs.tris.begin() + B.triStart + B.triCount); n = B.triCount; info[0] = B.triStart; }
+      else n = ctx->renderer->probeFastBvh(fast_index, tris, nodes, info);
+      break;
+    }
+    if (n < 0) return -1;
+    for (long long i = 0; i < n && i < cap_tris; ++i) { if (verts9) std::memcpy(verts9 + 9 * i, tris[i].v, 72); if (prim_serial) prim_serial[i] = hs.prims[tris[i].prim].serial; }
+    // links: >= 0 inner node (relative to the BVH's first LBVH node), < 0: -(1 + leaf number), leaf j = triangles 4j .. 4j+3 of the resident order
+    if (n <= cap_tris) for (size_t i = 0; i < nodes.size(); ++i) { const FNode& N = nodes[i];
+      if (links2) { links2[2 * i] = N.left >= 0 ? N.left - info[1] : -(1 + ((N.triL >> 3) - info[0]) / 4); links2[2 * i + 1] = N.right >= 0 ? N.right - info[1] : -(1 + ((N.triR >> 3) - info[0]) / 4); }
+      if (boxes12) std::memcpy(boxes12 + 12 * i, N.lmin, 96); }
+    return n;
+  } catch (std::exception& e) { ctx->err = e.what(); return DRT_ERR_SCENE; }
+}
 int drt_scene_counts(drt_ctx* ctx, int64_t* o) {
   GUARD(ctx, { if (!o) throw std::runtime_error("null output"); ctx->scene->finalize(); const HostScene& s = *ctx->scene; std::memset(o, 0, 8 * sizeof(int64_t));
     o[0] = (int64_t)s.tris.size(); for (const FBvh& B : s.bvhs) if (B.fast) { ++o[1]; o[3] += B.triCount; } for (const FPrim& P : s.prims) if (P.pad0 >= 0) ++o[2];

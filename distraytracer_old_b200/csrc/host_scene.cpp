@@ -249,6 +249,20 @@ void HostScene::addPrimitive(const Tokens& k) {                                /
     int type = PT_HCYL;
     if (c != "hollow_cylinder") { type = PT_CYL; double caps[8] = {ox, oy, oz, -yTop, ox, -oy, oz, yBot}; d.insert(d.end(), caps, caps + 8); }
     addGeom(makePrim(type, 0, d, v3(x, y, z), v3(x + -ext, y + 0, z + -ext), v3(x + ext, y + h, z + ext)), false);
+  } else if (c == "torus") {
+    // torus R r [facets] x y z : centre (x,y,z), axis = object-space y, major radius R (myTorus.bodyRad), tube radius r (ringRad); the optional third
+    // number of data/c2torus.cli (the facet count of the reference's abandoned polygonal torus) is accepted and ignored
+    const bool six = k.size() >= 7; const double R = k.num(1), r = k.num(2), x = k.num(six ? 4 : 3), y = k.num(six ? 5 : 4), z = k.num(six ? 6 : 5), ext = R + r;
+    addGeom(makePrim(PT_TORUS, 0, {x, y, z, R, r}, v3(x, y, z), v3(x + -ext, y + -r, z + -ext), v3(x + ext, y + r, z + ext)), false);
+  } else if (c == "quadric") {
+    // quadric a b c d e f g h i j [xmin ymin zmin xmax ymax zmax] : a x^2 + b y^2 + c z^2 + d xy + e xz + f yz + g x + h y + i z + j = 0 (the ten
+    // coefficients of src/tmpQuadricEQ.txt), kept inside the optional clip box
+    std::vector<double> d; for (int i = 1; i <= 10; ++i) d.push_back(k.num(i));
+    double bx[6] = {-100000, -100000, -100000, 100000, 100000, 100000};
+    if (k.size() >= 17) for (int i = 0; i < 6; ++i) bx[i] = k.num(11 + i);
+    for (int i = 0; i < 3; ++i) if (bx[i] > bx[3 + i]) std::swap(bx[i], bx[3 + i]);
+    d.insert(d.end(), bx, bx + 6);
+    addGeom(makePrim(PT_QUADRIC, 0, d, v3((bx[0] + bx[3]) * .5, (bx[1] + bx[4]) * .5, (bx[2] + bx[5]) * .5), v3(bx[0], bx[1], bx[2]), v3(bx[3], bx[4], bx[5])), false);
   } else if (c == "plane") {
     // myPlane.setPlaneVals (myPlanarObject.java:236-270) + the two states invertNormal() would produce (:71-88)
     double a = k.num(1), b = k.num(2), cc = k.num(3), dd = k.num(4);
@@ -534,6 +548,11 @@ void HostScene::command(const std::string& line) {
     else if (c == "vertex") { if (poly_.active && poly_.cnt < poly_.n) { poly_.v[poly_.cnt][0] = k.num(1); poly_.v[poly_.cnt][1] = k.num(2); poly_.v[poly_.cnt][2] = k.num(3); } poly_.cnt++; }
     else if (c == "end") { endPoly(); vertType_ = "triangle"; }
     else if (c == "box" || c == "plane" || c == "cyl" || c == "cylinder" || c == "hollow_cylinder" || c == "sphere" || c == "moving_sphere" || c == "sphereIn" || c == "ellipsoid") addPrimitive(k);
+    // ---- extension primitives (north star: "quadrics, tori").  The reference has no reader command for either and its myTorus never reports a hit
+    // (myImpObject.java:330-390; notes in src/tmpQuadricEQ.txt), so a drop-in must ignore these lines -- which is what happens unless the scene
+    // itself says `extensions on` (a line the reference ignores as well).  Semantics are this project's own: parity unpinned.
+    else if (c == "extensions") { extensions_ = (k.size() < 2 || lowered(k.str(1)) != "off"); }
+    else if ((c == "torus" || c == "quadric") && extensions_) addPrimitive(k);
     else if (c == "push") push();
     else if (c == "pop") pop();
     else if (c == "rotate") rotate(k.num(1), k.num(2), k.num(3), k.num(4));

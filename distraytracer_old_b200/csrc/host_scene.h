@@ -89,6 +89,7 @@ class HostScene {
   struct Mat { V3 diff, amb, spec, perm, kreflClr; double phong = 0, krefl = 0, ktrans = 0, rfrIdx = 0; } mat_;
   int txtrType_ = 0; double noiseScale_ = 1; std::vector<V3> noiseColors_; int numOctaves_ = 8; double turbMult_ = 1, colorScale_ = 10, colorMult_ = .2; V3 pdMult_;
   bool rndColors_ = false, useCustClrs_ = false, useFwdTrans_ = false; double avgNumPerCell_ = 1, mortarThresh_ = .04; int numPtsDist_ = 2, distFunc_ = 1, roiFunc_ = 1;
+  bool extensions_ = false;           // `extensions on`: torus / quadric commands are honoured (the reference ignores both lines)
   bool simpleRefr_ = false, txtrdTop_ = false, txtrdBtm_ = false, usePhotonMap_ = false, isCausticPhtn_ = false;
   int curTopImage_ = -1;
   void setSurface(V3 d, V3 a, V3 s, double ph, double kr);

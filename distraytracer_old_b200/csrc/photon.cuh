@@ -182,9 +182,10 @@ __global__ void k_photon_cellkeys(const PhotonRec* __restrict__ rec, long long n
   keys[i] = key; atomicAdd(&cellCount[key], 1u);
 }
 // sorted order -> the two 32-byte-per-photon arrays the gather reads with 128-bit loads
-__global__ void k_photon_reorder(const PhotonRec* __restrict__ rec, const uint32_t* __restrict__ order, long long n, double4* __restrict__ pos, double4* __restrict__ pwr) {
+// (+ a float4 mirror of the positions for the gather's FP32 pre-test, see phWarpGather32)
+__global__ void k_photon_reorder(const PhotonRec* __restrict__ rec, const uint32_t* __restrict__ order, long long n, double4* __restrict__ pos, double4* __restrict__ pwr, float4* __restrict__ pos32) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
-  const PhotonRec r = rec[order[i]]; pos[i] = make_double4(r.x, r.y, r.z, 0.0); pwr[i] = make_double4(r.r, r.g, r.b, 0.0);
+  const PhotonRec r = rec[order[i]]; pos[i] = make_double4(r.x, r.y, r.z, 0.0); pwr[i] = make_double4(r.r, r.g, r.b, 0.0); pos32[i] = make_float4((float)r.x, (float)r.y, (float)r.z, 0.0f);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -194,8 +195,16 @@ __global__ void k_photon_reorder(const PhotonRec* __restrict__ rec, const uint32
 #define DRT_PH_LANE_MAX 1024u     // candidate count up to which a lane serves its own query
 #endif
 #define DRT_PH_BINS 256
+#ifndef DRT_PH_TIGHT
+#define DRT_PH_TIGHT 1           // search plans shrink their radius to the expected k-th neighbour distance (phMakePlan)
+#endif
+#ifndef DRT_PH_FP32
+#define DRT_PH_FP32 1            // warp tier: FP32 pre-test selection first (phWarpGather32), FP64 radix select as the fallback
+#endif
 #define DRT_PH_LIST 128
-struct PhWarpShared { uint32_t hist[DRT_PH_BINS]; double listD2[DRT_PH_LIST]; uint32_t listIdx[DRT_PH_LIST]; uint32_t listN; uint32_t pad[3]; };
+#define DRT_PH_MAXRANGES 160      // candidate ranges of one query: <= 7 x 7 fine rows x 3 runs (fine cube of half-width 3), <= 3 x 3 coarse rows
+struct PhWarpShared { uint32_t hist[DRT_PH_BINS]; double listD2[DRT_PH_LIST]; uint32_t listIdx[DRT_PH_LIST]; uint32_t listN; uint32_t pad[3];
+                      uint32_t rA[DRT_PH_MAXRANGES + 33], rOff[DRT_PH_MAXRANGES + 33]; };     // non-empty candidate ranges: first photon, exclusive prefix of the lengths (+ sentinels)
 
 // Sum of the powers of the k nearest photons with d^2 < r^2 around p, and the largest of their d^2 -- computed by one warp.
 // Selection = radix select on a 32-bit quantisation of d^2 (monotone in d^2), 8 bits per level over the candidate rows of the grid,
@@ -221,7 +230,7 @@ __device__ inline bool phWarpGather(const DScene& S, D3 p, double r2, bool needA
   const double4* __restrict__ P = reinterpret_cast<const double4*>(S.phPos); const double4* __restrict__ W = reinterpret_cast<const double4*>(S.phPwr);
   // visit every candidate; F(j, d2, q, ok) is called warp-wide, ok = d2 < r2.  Two shapes of candidate set:
   //   coarse (fineHalf < 0): the <= 3x3 rows of coarse cells lo..hi the r-sphere's bounding cube overlaps, one contiguous photon range per row
-  //   fine   (fineHalf = s): the (2s+1)^3 fine sub-cells around the fine cell lo[] that contains p (every photon within s fine cells of p)
+  //   fine   (fineHalf >= 0): the block of fine sub-cells lo..hi the plan's search sphere overlaps (see phMakePlan)
   auto scan = [&](uint32_t a, uint32_t b, auto&& F) {
     for (uint32_t j0 = a; j0 < b; j0 += 32) {
       const uint32_t j = j0 + lane; bool ok = j < b; double d2 = 0;
@@ -236,8 +245,7 @@ __device__ inline bool phWarpGather(const DScene& S, D3 p, double r2, bool needA
         scan(S.cellStart[(size_t)(row + lo[0]) << 6], S.cellStart[(size_t)(row + hi[0] + 1) << 6], F);
       }
     } else {
-      const int fdx = 4 * (int)S.gridDim[0], fdy = 4 * (int)S.gridDim[1], fdz = 4 * (int)S.gridDim[2];
-      const int z0 = max(lo[2] - fineHalf, 0), z1 = min(lo[2] + fineHalf, fdz - 1), y0 = max(lo[1] - fineHalf, 0), y1 = min(lo[1] + fineHalf, fdy - 1), x0 = max(lo[0] - fineHalf, 0), x1 = min(lo[0] + fineHalf, fdx - 1);
+      const int z0 = lo[2], z1 = hi[2], y0 = lo[1], y1 = hi[1], x0 = lo[0], x1 = hi[0];          // fine-cell bounds of the plan (inclusive, inside the grid)
       for (int fz = z0; fz <= z1; ++fz) for (int fy = y0; fy <= y1; ++fy) {
         const uint32_t crow = ((uint32_t)(fz >> 2) * S.gridDim[1] + (uint32_t)(fy >> 2)) * S.gridDim[0], sub = ((uint32_t)(fz & 3) << 4) | ((uint32_t)(fy & 3) << 2);
         for (int fx = x0; fx <= x1; ) {          // fine cells of one coarse cell that share (fy, fz) are consecutive keys: one range per run
@@ -316,6 +324,157 @@ __device__ inline bool phWarpGather(const DScene& S, D3 p, double r2, bool needA
   return true;
 }
 
+// The candidate ranges of one query, as contiguous photon index ranges: G(a, b) per range.  Two shapes of candidate set, as in phWarpGather.
+template <class G_>
+__device__ __forceinline__ void phForRanges(const DScene& S, int fineHalf, const int lo[3], const int hi[3], G_&& G) {
+  if (fineHalf < 0) {
+    for (int cz = lo[2]; cz <= hi[2]; ++cz) for (int cy = lo[1]; cy <= hi[1]; ++cy) {
+      const uint32_t row = ((uint32_t)cz * S.gridDim[1] + (uint32_t)cy) * S.gridDim[0];
+      G(S.cellStart[(size_t)(row + lo[0]) << 6], S.cellStart[(size_t)(row + hi[0] + 1) << 6]);
+    }
+  } else {
+    const int z0 = lo[2], z1 = hi[2], y0 = lo[1], y1 = hi[1], x0 = lo[0], x1 = hi[0];
+    for (int fz = z0; fz <= z1; ++fz) for (int fy = y0; fy <= y1; ++fy) {
+      const uint32_t crow = ((uint32_t)(fz >> 2) * S.gridDim[1] + (uint32_t)(fy >> 2)) * S.gridDim[0], sub = ((uint32_t)(fz & 3) << 4) | ((uint32_t)(fy & 3) << 2);
+      for (int fx = x0; fx <= x1; ) {
+        const int runEnd = min(x1, fx | 3); const size_t k0 = ((size_t)(crow + (uint32_t)(fx >> 2)) << 6) | sub | (uint32_t)(fx & 3);
+        G(S.cellStart[k0], S.cellStart[k0 + (size_t)(runEnd - fx) + 1]);
+        fx = runEnd + 1;
+      }
+    }
+  }
+}
+// FP32 pre-test form of phWarpGather: the same exact result from ONE histogram pass and one collection pass, both in FP32.
+// The FP64 selection above re-reads every candidate's 32-byte position and re-forms d^2 in FP64 for every radix level (2-3 scans of ~11 FP64-pipe
+// operations per candidate: the half-rate FP64 pipe is what bounds dense maps).  Here d^2 is formed in FP32 from a float4 mirror of the positions;
+// with u = 2^-24, A = largest |coordinate| of a photon and rho = sqrt(r2),
+//     |d2_32 - d2| <= delta = 2 sqrt(3) rho e + 3 e^2 + 4 u r2,     e = u (|p|_inf + A + rho)        (coordinate rounding + one rounding per operation)
+// for every candidate with d2 <= r2.  256 bins of width w = r2/256 over the FP32 values; the method is used only if 4 delta < w.  Then, with b the
+// bin where the running count reaches k: every candidate binned <= b-2 is among the k nearest (the k-th true distance is >= edge(b) - delta),
+// every candidate binned >= b+2 is not, and the <= 128 candidates of bins b-1..b+1 are resolved exactly -- FP64 d^2 from the FP64 positions,
+// (d^2, index) order -- exactly as the boundary list of phWarpGather.  The k-th neighbour itself is always in that list, so the d^2 that leaves the
+// function is the FP64 value.  Candidates within delta of the radius are classified by their FP64 d^2.  Returns 1 (done), 0 (needAll and fewer
+// than k photons inside r2) or -1 (margin too wide, or a boundary list longer than 128: the caller runs phWarpGather).
+__device__ inline int phWarpGather32(const DScene& S, D3 p, double r2, bool needAll, int fineHalf, const int lo[3], const int hi[3], PhWarpShared& sh, double sum[3], double& dmax2) {
+  const unsigned lane = threadIdx.x & 31; const int K = S.g.kNhood;
+  sum[0] = sum[1] = sum[2] = 0; dmax2 = 0;
+  if (S.numPhotons == 0 || K <= 0) return 1;
+  const float u = 5.9604644775390625e-8f, rho = __double2float_ru(sqrt(r2)), r2f = __double2float_ru(r2);
+  const float pm = fmaxf(fmaxf(fabsf(__double2float_ru(fabs(p.x))), fabsf(__double2float_ru(fabs(p.y)))), fabsf(__double2float_ru(fabs(p.z))));
+  const float e = 1.01f * u * (pm + S.phAbsMax + rho), delta = 1.05f * (3.4641016f * rho * e + 3.0f * e * e + 4.0f * u * r2f);
+  if (!(4.0f * delta < r2f * (1.0f / 256.0f)) || !(r2f < 1e30f) || !(r2f > 1e-30f)) return -1;
+  const float rIn = __double2float_rd(r2) - delta, rOut = r2f + delta, scale = 256.0f / r2f, px = (float)p.x, py = (float)p.y, pz = (float)p.z;
+  const float4* __restrict__ P32 = reinterpret_cast<const float4*>(S.phPos32);
+  const double4* __restrict__ P = reinterpret_cast<const double4*>(S.phPos); const double4* __restrict__ W = reinterpret_cast<const double4*>(S.phPwr);
+  auto exactD2 = [&](uint32_t j) { const double4 q = P[j]; const double dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z; return dx * dx + dy * dy + dz * dz; };
+  // bin of candidate j, or -1 when it is outside the radius
+  auto binOf = [&](uint32_t j) -> int {
+    const float4 q = P32[j]; const float dx = px - q.x, dy = py - q.y, dz = pz - q.z; const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    if (d2 > rOut) return -1;
+    if (d2 >= rIn && !(exactD2(j) < r2)) return -1;
+    const int b = (int)(d2 * scale); return b > 255 ? 255 : b;
+  };
+  for (int i = lane; i < DRT_PH_BINS; i += 32) sh.hist[i] = 0;
+  if (lane == 0) sh.listN = 0;
+  __syncwarp();
+  // ---- the candidate ranges, enumerated lane-parallel and compacted (empty ones dropped) into shared memory with the running offset of each:
+  // a fine row run holds ~10-30 photons, so looping "per range, 32 lanes over its photons" left two thirds of the lanes idle and spent 40 % of
+  // the instructions on warp-uniform range bookkeeping (profiles/r2d_ncu_gather.md).  The two passes below walk the FLAT candidate index instead.
+  uint32_t nRanges = 0, total = 0;
+  {
+    const int x0 = lo[0], x1 = hi[0], y0 = lo[1], y1 = hi[1], z0 = lo[2], z1 = hi[2], nx = fineHalf < 0 ? 1 : (x1 >> 2) - (x0 >> 2) + 1;     // coarse rows, or runs of fine cells
+    const int ny = y1 - y0 + 1, nz = z1 - z0 + 1, slots = nx * ny * nz;
+    if (slots > DRT_PH_MAXRANGES || slots <= 0) return -1;
+    for (int s0 = 0; s0 < slots; s0 += 32) {
+      const int slot = s0 + (int)lane; uint32_t a = 0, len = 0;
+      if (slot < slots) {
+        const int ir = slot % nx, iy = (slot / nx) % ny, iz = slot / (nx * ny); const int fy = y0 + iy, fz = z0 + iz;
+        if (fineHalf < 0) { const uint32_t row = ((uint32_t)fz * S.gridDim[1] + (uint32_t)fy) * S.gridDim[0]; a = S.cellStart[(size_t)(row + x0) << 6]; len = S.cellStart[(size_t)(row + x1 + 1) << 6] - a; }
+        else {
+          const int fx = ir == 0 ? x0 : (((x0 >> 2) + ir) << 2), runEnd = min(x1, fx | 3);
+          const uint32_t crow = ((uint32_t)(fz >> 2) * S.gridDim[1] + (uint32_t)(fy >> 2)) * S.gridDim[0], sub = ((uint32_t)(fz & 3) << 4) | ((uint32_t)(fy & 3) << 2);
+          const size_t k0 = ((size_t)(crow + (uint32_t)(fx >> 2)) << 6) | sub | (uint32_t)(fx & 3);
+          a = S.cellStart[k0]; len = S.cellStart[k0 + (size_t)(runEnd - fx) + 1] - a;
+        }
+      }
+      const unsigned ne = __ballot_sync(0xffffffffu, len > 0);
+      uint32_t incl = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
+      if (len > 0) { const uint32_t at = nRanges + __popc(ne & ((1u << lane) - 1u)); sh.rA[at] = a; sh.rOff[at] = total + incl - len; }
+      nRanges += __popc(ne); total += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    for (uint32_t i = nRanges + lane; i < nRanges + 33; i += 32) { sh.rA[i] = 0; sh.rOff[i] = 0xFFFFFFFFu; }       // sentinels: "starts beyond everything"
+  }
+  __syncwarp();
+  // F(j, valid) for every candidate, 32 consecutive flat indices per step.  base = range holding flat index t0; the ranges that start inside
+  // (t0, t0 + 32) are among the next 32 (every range is non-empty), each lane looks at one of them: OR of their start bits -> owner of every lane.
+  auto flat = [&](auto&& F) {
+    if (total >= 64u * nRanges) {            // long ranges (coarse rows of a sparse map): the plain per-range loop wastes nothing and needs no search
+      for (uint32_t r = 0; r < nRanges; ++r) { const uint32_t a = sh.rA[r], b = a + (sh.rOff[r + 1] == 0xFFFFFFFFu ? total - sh.rOff[r] : sh.rOff[r + 1] - sh.rOff[r]);
+        for (uint32_t j0 = a; j0 < b; j0 += 32) F(j0 + lane, j0 + lane < b); }
+      return;
+    }
+    uint32_t base = 0;
+    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+      const uint32_t rel = sh.rOff[base + 1 + lane] - t0;                      // >= 1
+      const unsigned mask = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+      const uint32_t owner = base + __popc(mask & ((2u << lane) - 1u)), t = t0 + lane;
+      F(sh.rA[owner] + (t - sh.rOff[owner]), t < total);
+      base += __popc(__ballot_sync(0xffffffffu, rel <= 32u));
+    }
+  };
+  unsigned m = 0;
+  flat([&](uint32_t j, bool valid) { const int bin = valid ? binOf(j) : -1; if (bin >= 0) atomicAdd(&sh.hist[bin], 1u); m += __popc(__ballot_sync(0xffffffffu, bin >= 0)); });
+  __syncwarp();
+  if (needAll && (int)m < K) return 0;
+  if (m == 0) return 1;
+  // boundary bin b: running count reaches k (m > k), or the highest non-empty bin (m <= k: every photon inside r2 is taken)
+  uint32_t loc[8], s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { loc[i] = sh.hist[lane * 8 + i]; s += loc[i]; }
+  uint32_t incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
+  const uint32_t target = (int)m > K ? (uint32_t)K : m;
+  const unsigned reach = __ballot_sync(0xffffffffu, incl >= target); const int L = __ffs(reach) - 1;
+  int bSel = 0;
+  if ((int)lane == L) { uint32_t c = incl - s; for (int i = 0; i < 8; ++i) { if (c + loc[i] >= target) { bSel = (int)lane * 8 + i; break; } c += loc[i]; } }
+  bSel = __shfl_sync(0xffffffffu, bSel, L);
+  const int bLo = bSel - 1, bHi = bSel + 1;                  // exact zone; bins < bLo are in, bins > bHi are out
+  uint32_t below = 0, zone = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const int bin = (int)lane * 8 + i; if (bin < bLo) below += loc[i]; else if (bin <= bHi) zone += loc[i]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { below += __shfl_xor_sync(0xffffffffu, below, o); zone += __shfl_xor_sync(0xffffffffu, zone, o); }
+  if (zone > DRT_PH_LIST) return -1;
+  const int need = (int)target - (int)below;                 // >= 1: the running count through bin b-1 is below the target
+  double s0 = 0, s1 = 0, s2 = 0, mx = 0;
+  flat([&](uint32_t j, bool valid) {
+    const int bin = valid ? binOf(j) : -1;
+    if (bin >= 0 && bin < bLo) { const double4 w = W[j]; s0 += w.x; s1 += w.y; s2 += w.z; }
+    const bool bnd = bin >= bLo && bin <= bHi; const unsigned bm = __ballot_sync(0xffffffffu, bnd);
+    if (bm) {
+      if (bnd) { const uint32_t at = sh.listN + __popc(bm & ((1u << lane) - 1u)); sh.listD2[at] = exactD2(j); sh.listIdx[at] = j; }
+      __syncwarp();
+      if (lane == 0) sh.listN += __popc(bm);
+      __syncwarp();
+    }
+  });
+  __syncwarp();
+  const int n = (int)sh.listN;
+  for (int i = lane; i < n; i += 32) {
+    const double di = sh.listD2[i]; const uint32_t ji = sh.listIdx[i]; int rank = 0;
+    for (int t = 0; t < n; ++t) { const double dt = sh.listD2[t]; rank += (dt < di || (dt == di && sh.listIdx[t] < ji)) ? 1 : 0; }
+    if (rank < need) { const double4 w = W[ji]; s0 += w.x; s1 += w.y; s2 += w.z; mx = fmax(mx, di); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  __syncwarp();
+  sum[0] = s0; sum[1] = s1; sum[2] = s2; dmax2 = mx;
+  return 1;
+}
+
 // cheap per-lane test: does any cell the search sphere's bounding cube overlaps hold a photon at all?  (sparse caustic maps: most queries do not)
 __device__ inline uint32_t phCountCandidates(const DScene& S, const int lo[3], const int hi[3]) {
   uint32_t c = 0;
@@ -330,7 +489,7 @@ __device__ inline uint32_t phCountCandidates(const DScene& S, const int lo[3], c
 //   inscribed search sphere gives the plan
 //   "search radius s * fineCell over that cube" -- exact if >= k photons turn out to lie inside that radius (every photon closer than s fine
 //   cells to p is in the cube), otherwise the caller falls back to the full radius over the coarse rows.
-struct PhPlan { int fineHalf; int c[3]; int h[3]; double r2; };      // fineHalf < 0: coarse rows c..h with threshold r2
+struct PhPlan { int fineHalf; int c[3]; int h[3]; double r2; int f[3]; double r2max; bool shrunk; };      // fineHalf < 0: coarse rows c..h, else fine cells c..h with threshold r2; f / r2max: the un-shrunk plan (cube f +- fineHalf, radius of fineHalf fine cells)
 __device__ __forceinline__ uint32_t phCountFineCube(const DScene& S, const int f[3], int s) {
   const int fdx = 4 * (int)S.gridDim[0], fdy = 4 * (int)S.gridDim[1], fdz = 4 * (int)S.gridDim[2];
   const int z0 = max(f[2] - s, 0), z1 = min(f[2] + s, fdz - 1), y0 = max(f[1] - s, 0), y1 = min(f[1] + s, fdy - 1), x0 = max(f[0] - s, 0), x1 = min(f[0] + s, fdx - 1);
@@ -342,22 +501,35 @@ __device__ __forceinline__ uint32_t phCountFineCube(const DScene& S, const int f
   }
   return c;
 }
+// The plan: a search radius rho <= s fine cells (s = 1, 2, 3) and the block of fine cells its sphere's bounding cube overlaps.  s = the first
+// half-width whose cube is expected to hold >= 1.25 k photons inside its inscribed sphere (surface distribution: share pi s^2 / (2s+1)^2); rho is
+// then shrunk from s fine cells to the radius expected to hold 1.5 k photons under the same area scaling -- the scanned block shrinks with it,
+// from (2s+1)^3 cells to the cells [p - rho, p + rho] touches.  Exact whatever the estimate: a plan's result is used only if >= k photons turn
+// out to lie inside rho (then the k nearest are among them, and every photon inside rho is in a scanned cell); otherwise the caller searches the
+// full radius over the coarse rows.
 __device__ __forceinline__ void phMakePlan(const DScene& S, D3 p, uint32_t coarseCount, const int lo[3], const int hi[3], PhPlan& pl) {
-  const int K = S.g.kNhood; pl.fineHalf = -1; pl.r2 = S.g.phMaxDist2;
-  for (int k = 0; k < 3; ++k) { pl.c[k] = lo[k]; pl.h[k] = hi[k]; }
+  const int K = S.g.kNhood; pl.fineHalf = -1; pl.r2 = S.g.phMaxDist2; pl.r2max = pl.r2; pl.shrunk = false;
+  for (int k = 0; k < 3; ++k) { pl.c[k] = lo[k]; pl.h[k] = hi[k]; pl.f[k] = 0; }
   if (coarseCount < (uint32_t)(8 * K)) return;
   const double cf = S.cellSize * 0.25, pp[3] = {p.x, p.y, p.z}; int f[3]; bool inside = true;
   for (int k = 0; k < 3; ++k) { const double a = floor((pp[k] - S.gridMin[k]) / cf); const int fd = 4 * (int)S.gridDim[k]; if (!(a >= 0) || !(a <= fd - 1)) inside = false; f[k] = (int)a; }
   if (!inside) return;
-  // expected share of a cube's photons that lie inside the sphere of radius s fine cells (surface distribution): pi s^2 / (2s+1)^2
   const double frac[4] = {0.0, 0.349, 0.503, 0.577};
   for (int s = 1; s <= 3; ++s) {
-    const double rad = s * cf * (1.0 - 1e-6);                                  // 1e-6: a photon's own fine index is a rounded quotient
-    if (!(rad * rad <= S.g.phMaxDist2)) return;                                // never search beyond the scene's radius (find_near requires d^2 < r^2): when the
+    const double radMax = s * cf * (1.0 - 1e-6);                               // 1e-6: a photon's own fine index is a rounded quotient
+    if (!(radMax * radMax <= S.g.phMaxDist2)) return;                          // never search beyond the scene's radius (find_near requires d^2 < r^2): when the
                                                                                // grid had to double its cell size the fine cells are wider than r/4 and the plan does not apply
-    if ((double)phCountFineCube(S, f, s) * frac[s] >= 1.25 * K) {
-      pl.fineHalf = s; for (int k = 0; k < 3; ++k) { pl.c[k] = f[k]; pl.h[k] = s; }
-      pl.r2 = rad * rad; return;
+    const double inSphere = (double)phCountFineCube(S, f, s) * frac[s];
+    if (inSphere >= 1.25 * K) {
+      double rad = radMax * sqrt(1.5 * K / inSphere); if (!(rad < radMax)) rad = radMax;
+#if !DRT_PH_TIGHT
+      rad = radMax;
+#endif
+      const double reach = rad * (1.0 + 1e-6) + 1e-9 * cf;                     // cells the sphere can touch, with room for the rounding of a photon's own cell index
+      pl.fineHalf = s; pl.r2 = rad * rad; pl.r2max = radMax * radMax; pl.shrunk = rad < radMax;
+      for (int k = 0; k < 3; ++k) { const int fd = 4 * (int)S.gridDim[k]; const int a = (int)floor((pp[k] - reach - S.gridMin[k]) / cf), b = (int)floor((pp[k] + reach - S.gridMin[k]) / cf);
+        pl.c[k] = max(max(a, f[k] - s), 0); pl.h[k] = min(min(b, f[k] + s), fd - 1); pl.f[k] = f[k]; }
+      return;
     }
   }
 }
@@ -430,7 +602,7 @@ __device__ inline bool phLaneTiers(const DScene& S, bool needs, D3 loc, PhLaneSh
 // tier 3 / 4: the warp serves its pending queries one at a time
 __device__ inline void phWarpTier(const DScene& S, bool pending, D3 loc, PhWarpTierShared& sm, double sum[3], double& dmax2, int* path) {
   const unsigned lane = threadIdx.x & 31; const double r2 = S.g.phMaxDist2; const int K = S.g.kNhood;
-  bool few = false; int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; PhPlan pl; pl.fineHalf = -1; pl.r2 = r2; for (int k = 0; k < 3; ++k) pl.c[k] = pl.h[k] = 0;
+  bool few = false; int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; PhPlan pl; pl.fineHalf = -1; pl.r2 = r2; pl.r2max = r2; pl.shrunk = false; for (int k = 0; k < 3; ++k) pl.c[k] = pl.h[k] = pl.f[k] = 0;
   bool needs = pending && S.numPhotons > 0 && K > 0;
   if (needs) { needs = phCellRange(S, loc, r2, lo, hi); const uint32_t cnt = needs ? phCountCandidates(S, lo, hi) : 0u; needs = cnt > 0; few = cnt <= (uint32_t)K; if (needs) phMakePlan(S, loc, cnt, lo, hi, pl); }
   unsigned mask = __ballot_sync(0xffffffffu, needs);
@@ -442,13 +614,22 @@ __device__ inline void phWarpTier(const DScene& S, bool pending, D3 loc, PhWarpT
     if (fineHalf > 0) {
       const double pr2 = __shfl_sync(0xffffffffu, pl.r2, src);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { qlo[k] = __shfl_sync(0xffffffffu, pl.c[k], src); qhi[k] = fineHalf; }
-      done = phWarpGather(S, p, pr2, true, false, fineHalf, qlo, qhi, sm.warp[threadIdx.x >> 5], qs, qd, nullptr);
+      for (int k = 0; k < 3; ++k) { qlo[k] = __shfl_sync(0xffffffffu, pl.c[k], src); qhi[k] = __shfl_sync(0xffffffffu, pl.h[k], src); }
+      const int g32 = DRT_PH_FP32 ? phWarpGather32(S, p, pr2, true, fineHalf, qlo, qhi, sm.warp[threadIdx.x >> 5], qs, qd) : -1;
+      done = g32 > 0 || (g32 < 0 && phWarpGather(S, p, pr2, true, false, fineHalf, qlo, qhi, sm.warp[threadIdx.x >> 5], qs, qd, nullptr));
+      if (!done && __shfl_sync(0xffffffffu, (int)pl.shrunk, src) != 0) {      // fewer than k photons inside the shrunk radius: the plan's full radius over its whole cube, before the coarse rows
+        const double pr2m = __shfl_sync(0xffffffffu, pl.r2max, src);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const int fk = __shfl_sync(0xffffffffu, pl.f[k], src); qlo[k] = max(fk - fineHalf, 0); qhi[k] = min(fk + fineHalf, 4 * (int)S.gridDim[k] - 1); }
+        const int g2 = DRT_PH_FP32 ? phWarpGather32(S, p, pr2m, true, fineHalf, qlo, qhi, sm.warp[threadIdx.x >> 5], qs, qd) : -1;
+        done = g2 > 0 || (g2 < 0 && phWarpGather(S, p, pr2m, true, false, fineHalf, qlo, qhi, sm.warp[threadIdx.x >> 5], qs, qd, nullptr));
+      }
     }
     if (!done) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) { qlo[k] = __shfl_sync(0xffffffffu, lo[k], src); qhi[k] = __shfl_sync(0xffffffffu, hi[k], src); }
-      phWarpGather(S, p, r2, false, __shfl_sync(0xffffffffu, (int)few, src) != 0, -1, qlo, qhi, sm.warp[threadIdx.x >> 5], qs, qd, nullptr);
+      const int g32 = DRT_PH_FP32 ? phWarpGather32(S, p, r2, false, -1, qlo, qhi, sm.warp[threadIdx.x >> 5], qs, qd) : -1;
+      if (g32 < 0) phWarpGather(S, p, r2, false, __shfl_sync(0xffffffffu, (int)few, src) != 0, -1, qlo, qhi, sm.warp[threadIdx.x >> 5], qs, qd, nullptr);
     }
     if ((int)lane == src) { sum[0] = qs[0]; sum[1] = qs[1]; sum[2] = qs[2]; dmax2 = qd; if (path) *path = done ? 4 : 3; }
     __syncwarp();
@@ -491,12 +672,13 @@ __global__ void __launch_bounds__(128) k_photon_gather_warp(const __grid_constan
 
 // parity probe: the same routines at explicit points, one lane per point: out = {sum r,g,b, dmax2, tier taken}
 __global__ void __launch_bounds__(128) k_photon_probe(const __grid_constant__ DScene S, long long n, const double* __restrict__ pts, double* __restrict__ out) {
-  __shared__ PhLaneShared sl; __shared__ PhWarpTierShared sw;
+  __shared__ union ProbeShared { PhLaneShared sl; PhWarpTierShared sw; } u;       // the two tiers run one after the other (48 KB static limit)
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; const bool ok = q < n;
   const D3 p = ok ? d3(pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]) : d3(0, 0, 0);
   double sum[3], dmax2; int path = 0;
-  const bool pending = phLaneTiers(S, ok, p, sl, sum, dmax2, &path);
-  double s2[3], d2; int path2 = 0; phWarpTier(S, pending, p, sw, s2, d2, &path2);
+  const bool pending = phLaneTiers(S, ok, p, u.sl, sum, dmax2, &path);
+  __syncthreads();
+  double s2[3], d2; int path2 = 0; phWarpTier(S, pending, p, u.sw, s2, d2, &path2);
   if (pending) { sum[0] = s2[0]; sum[1] = s2[1]; sum[2] = s2[2]; dmax2 = d2; path = path2; }
   if (ok) { out[5 * q] = sum[0]; out[5 * q + 1] = sum[1]; out[5 * q + 2] = sum[2]; out[5 * q + 3] = dmax2; out[5 * q + 4] = (double)path; }
 }
@@ -507,7 +689,7 @@ __global__ void __launch_bounds__(128) k_photon_probe(const __grid_constant__ DS
 struct PhotonMap {
   bool built = false, emitted = false; unsigned long long count = 0, segments = 0;
   PhotonRec* rec = nullptr; size_t recCap = 0;                  // canonical-order records (emission output / grid input)
-  double4 *pos = nullptr, *pwr = nullptr; uint32_t* cellStart = nullptr; size_t sortedCap = 0, cellCap = 0;
+  double4 *pos = nullptr, *pwr = nullptr; float4* pos32 = nullptr; uint32_t* cellStart = nullptr; size_t sortedCap = 0, cellCap = 0;
   PhGrid grid{}; float msEmit = 0, msBuild = 0;
   // grow-only scratch (no cudaMalloc / cudaFree on the per-frame path: they cost tens to hundreds of ms when they hit the driver's slow path)
   struct Scratch { void* p = nullptr; size_t cap = 0; template <class T> T* get(size_t n) { const size_t b = n * sizeof(T); if (b > cap) { cudaFree(p); p = nullptr; cap = b + b / 4 + 4096; CK(cudaMalloc(&p, cap)); } return reinterpret_cast<T*>(p); }
@@ -516,7 +698,7 @@ struct PhotonMap {
   void events() { if (!evA) { CK(cudaEventCreate(&evA)); CK(cudaEventCreate(&evB)); } }
 
   void reset() { built = false; emitted = false; count = 0; segments = 0; }
-  void release() { cudaFree(rec); cudaFree(pos); cudaFree(pwr); cudaFree(cellStart); rec = nullptr; pos = pwr = nullptr; cellStart = nullptr; recCap = sortedCap = cellCap = 0; reset();
+  void release() { cudaFree(rec); cudaFree(pos); cudaFree(pwr); cudaFree(pos32); cudaFree(cellStart); rec = nullptr; pos = pwr = nullptr; pos32 = nullptr; cellStart = nullptr; recCap = sortedCap = cellCap = 0; reset();
     sSlots.release(); sCnt.release(); sOff.release(); sScan.release(); sHist.release(); sBounds.release(); for (int k = 0; k < 2; ++k) { sKeys[k].release(); sVals[k].release(); }
     if (evA) { cudaEventDestroy(evA); cudaEventDestroy(evB); evA = evB = nullptr; } }
   void ensureRec(size_t n, cudaStream_t st) {
@@ -559,7 +741,7 @@ struct PhotonMap {
   }
 
   void buildGrid(DScene& ds, cudaStream_t st) {
-    ds.numPhotons = 0; ds.phPos = nullptr; ds.phPwr = nullptr; ds.cellStart = nullptr; ds.cellEnd = nullptr; built = true; msBuild = 0;
+    ds.numPhotons = 0; ds.phPos = nullptr; ds.phPwr = nullptr; ds.cellStart = nullptr; ds.phPos32 = nullptr; ds.phAbsMax = 0; ds.padP = 0; built = true; msBuild = 0;
     if (count == 0) return;
     if (count >= 0xFFFFFFF0ull) throw std::runtime_error("photon map larger than 2^32 records");
     events(); cudaEvent_t e0 = evA, e1 = evB; CK(cudaEventRecord(e0, st));
@@ -580,7 +762,7 @@ struct PhotonMap {
     G.cell = cell; for (int k = 0; k < 3; ++k) G.gmin[k] = mn[k]; G.nCells = G.dim[0] * G.dim[1] * G.dim[2] * 64u; grid = G;     // nCells counts FINE cells
     // keys + per-cell counts, cellStart = exclusive scan (nCells + 1 entries: cellStart[nCells] = n)
     if ((size_t)G.nCells + 1 > cellCap) { cudaFree(cellStart); cellCap = (size_t)G.nCells + 1 + (size_t)G.nCells / 4; CK(cudaMalloc(&cellStart, cellCap * 4)); }
-    if ((size_t)n > sortedCap) { cudaFree(pos); cudaFree(pwr); sortedCap = (size_t)n + (size_t)n / 8 + 1024; CK(cudaMalloc(&pos, sortedCap * sizeof(double4))); CK(cudaMalloc(&pwr, sortedCap * sizeof(double4))); }
+    if ((size_t)n > sortedCap) { cudaFree(pos); cudaFree(pwr); cudaFree(pos32); sortedCap = (size_t)n + (size_t)n / 8 + 1024; CK(cudaMalloc(&pos, sortedCap * sizeof(double4))); CK(cudaMalloc(&pwr, sortedCap * sizeof(double4))); CK(cudaMalloc(&pos32, sortedCap * sizeof(float4))); }
     uint32_t *keys[2], *vals[2]; const long long nb = radixBlocks(n);
     for (int k = 0; k < 2; ++k) { keys[k] = sKeys[k].get<uint32_t>((size_t)n); vals[k] = sVals[k].get<uint32_t>((size_t)n); }
     const long long scanWords = std::max(scanScratchWords(256 * nb), scanScratchWords((long long)G.nCells + 1));
@@ -590,9 +772,10 @@ struct PhotonMap {
     scanExclusiveU32(cellStart, cellStart, (long long)G.nCells + 1, scratch, st);
     int bits = 1; while ((1ull << bits) < (unsigned long long)G.nCells) ++bits;
     const int cur = radixSortPairs(keys, vals, n, bits, true, hist, scratch, st);
-    k_photon_reorder<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, vals[cur], n, pos, pwr); ++g_kernelLaunches;
+    k_photon_reorder<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, vals[cur], n, pos, pwr, pos32); ++g_kernelLaunches;
     CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError()); CK(cudaEventElapsedTime(&msBuild, e0, e1));
-    ds.numPhotons = (uint32_t)n; ds.phPos = reinterpret_cast<const double*>(pos); ds.phPwr = reinterpret_cast<const double*>(pwr); ds.cellStart = cellStart; ds.cellEnd = nullptr;
+    ds.numPhotons = (uint32_t)n; ds.phPos = reinterpret_cast<const double*>(pos); ds.phPwr = reinterpret_cast<const double*>(pwr); ds.cellStart = cellStart; ds.phPos32 = reinterpret_cast<const float*>(pos32);
+    { double a = 0; for (int k = 0; k < 3; ++k) a = std::max(a, std::max(std::fabs(mn[k]), std::fabs(mx[k]))); const float f = (float)a; ds.phAbsMax = f >= a ? f : std::nextafter(f, INFINITY); ds.padP = 0; }
     for (int k = 0; k < 3; ++k) { ds.gridDim[k] = G.dim[k]; ds.gridMin[k] = G.gmin[k]; } ds.cellSize = G.cell;
   }
 

@@ -149,11 +149,14 @@ __device__ __forceinline__ double rayTime(const DScene& S, uint32_t stream, uint
 #ifndef DRT_LLIGHT_MINBLOCKS
 #define DRT_LLIGHT_MINBLOCKS 6
 #endif
+#ifndef DRT_L1_MINBLOCKS
+#define DRT_L1_MINBLOCKS 6           // lean variants for scenes with instanced meshes (F == TF_LITERAL1)
+#endif
 // Closest-hit pass of one level.  F = compile-time feature set (dev_isect.cuh): the lean variants defer what they cannot serve to `deferOut`;
 // the generic variant (TF_ALL) serves everything and is also the fix-up pass over such a list (`work` != null: ray indices to trace).
 // rays == null: level 0, the primary ray is generated from the index.
 template <bool COUNT, int F>
-__global__ void __launch_bounds__(128, (F == TF_ALL) ? DRT_TRACE_MINBLOCKS : DRT_LTRACE_MINBLOCKS)
+__global__ void __launch_bounds__(128, (F == TF_ALL) ? DRT_TRACE_MINBLOCKS : (F == TF_LITERAL1) ? DRT_L1_MINBLOCKS : DRT_LTRACE_MINBLOCKS)
 k_trace(const __grid_constant__ DScene S, Wave w, PixMap pm, long long pix0, const RayRec* __restrict__ rays, Hit* __restrict__ hits, Counters* ctr, const uint32_t* __restrict__ work, uint32_t* __restrict__ deferOut) {
   const long long n = work ? (long long)ctr->deferTrace[w.level] : waveCount(w, ctr);
   if (w.level == 0 && !work && blockIdx.x == 0 && threadIdx.x == 0) ctr->levelCount[0] = (unsigned long long)w.n0;
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(128, DRT_SHADE_MINBLOCKS) k_shade(const __grid
 // F / work / deferOut as in k_trace: a lean variant that meets a shadow ray it cannot serve leaves the WHOLE record to the generic pass
 // (the record's light sum is formed by one thread in list order either way).
 template <bool COUNT, int F>
-__global__ void __launch_bounds__(128, (F == TF_ALL) ? DRT_LIGHT_MINBLOCKS : DRT_LLIGHT_MINBLOCKS)
+__global__ void __launch_bounds__(128, (F == TF_ALL) ? DRT_LIGHT_MINBLOCKS : (F == TF_LITERAL1) ? DRT_L1_MINBLOCKS : DRT_LLIGHT_MINBLOCKS)
 k_light(const __grid_constant__ DScene S, Wave w, const SurfRec* __restrict__ surf, NodeRec* __restrict__ nodesBase, Counters* ctr, const uint32_t* __restrict__ work, uint32_t* __restrict__ deferOut) {
   const long long n = work ? (long long)ctr->deferLight[w.level] : waveCount(w, ctr);
   NodeRec* __restrict__ nodes = nodesBase + ((w.level == 0) ? 0 : waveNodeOffset(w, ctr, w.level));
@@ -473,6 +476,7 @@ struct Renderer::Impl {
   PhotonMap photons;
   size_t sceneBytes = 0;
   float lbvhMs = 0; long long lbvhTris = 0, lbvhNodes = 0;
+  std::vector<FBvh> bvhsUploaded;                // host copy of the FBvh array as uploaded (fastRoot points at the LBVH nodes in DRT_ACCEL_LBVH mode)
 };
 
 Renderer::Renderer(int device) : impl_(new Impl), device_(device) {
@@ -536,7 +540,7 @@ void Renderer::upload(const HostScene& hs, bool sameScene) {
   d.lists = A.put(hs.lists); d.nodes = A.put(hs.nodes); d.fnodes32 = A.put(hs.nodes32); d.tris = A.put(hs.tris); d.bvhs = A.put(bv); d.lights = A.put(hs.lights); d.shaders = A.put(hs.shaders);
   d.textures = A.put(hs.textures); d.texColors = A.put(hs.texColors); d.images = A.put(hs.images); d.texels = A.put(hs.texels);
   A.flush(st);
-  d.fnodes = d.nodes; impl_->lbvhMs = 0; impl_->lbvhTris = 0; impl_->lbvhNodes = 0;
+  d.fnodes = d.nodes; impl_->lbvhMs = 0; impl_->lbvhTris = 0; impl_->lbvhNodes = 0; impl_->bvhsUploaded = bv;
   if (extra) {
     const size_t n0 = hs.nodes.size();
     impl_->lbvhNodeBuf.ensure(n0 + extra, st); impl_->lbvhTriBuf.ensure(hs.tris.size(), st);
@@ -572,7 +576,7 @@ void Renderer::upload(const HostScene& hs, bool sameScene) {
   impl_->sceneBytes = A.used;                              // bytes copied host -> device by this upload
   d.g = hs.g; d.g.pad0 = 0;
   for (const FPrim& p : hs.prims) if (p.type == PT_MOVSPHERE) d.g.pad0 = 1;
-  d.numPhotons = 0; d.phPos = nullptr; d.phPwr = nullptr; d.cellStart = nullptr; d.cellEnd = nullptr;
+  d.numPhotons = 0; d.phPos = nullptr; d.phPwr = nullptr; d.cellStart = nullptr; d.phPos32 = nullptr; d.phAbsMax = 0; d.padP = 0;
   g_ = d.g;
   impl_->photons.reset();
   CK(cudaStreamSynchronize(st));
@@ -747,6 +751,17 @@ void Renderer::probePhotons(long long n, const double* ptsHost, double* out5Host
   if (I.ds.numPhotons > 0) k_photon_probe<<<gridFor(n, 128), 128, 0, st>>>(I.ds, n, a, b);
   CK(cudaMemcpyAsync(out5Host, b, n * 40, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
   cudaFree(a); cudaFree(b);
+}
+// parity probe: the resident packed triangles of fast BVH `fastIndex` and, in DRT_ACCEL_LBVH mode, its GPU-built nodes
+long long Renderer::probeFastBvh(int fastIndex, std::vector<FTri>& tris, std::vector<FNode>& nodes, int32_t info[4]) {
+  CK(cudaSetDevice(device_)); cudaStream_t st = (cudaStream_t)stream_; int k = 0;
+  for (const FBvh& B : impl_->bvhsUploaded) if (B.fast && k++ == fastIndex) {
+    tris.resize((size_t)B.triCount); if (B.triCount) CK(cudaMemcpyAsync(tris.data(), impl_->ds.tris + B.triStart, tris.size() * sizeof(FTri), cudaMemcpyDeviceToHost, st));
+    const bool lb = impl_->ds.accelMode == 2 && B.fastRoot != B.root; const int nn = lb ? (B.triCount + 3) / 4 - 1 : 0;
+    nodes.resize((size_t)nn); if (nn) CK(cudaMemcpyAsync(nodes.data(), impl_->ds.fnodes + B.fastRoot, nodes.size() * sizeof(FNode), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st)); info[0] = B.triStart; info[1] = B.fastRoot; info[2] = nn; info[3] = lb ? 1 : 0; return B.triCount;
+  }
+  return -1;
 }
 void Renderer::accelInfo(double out[4]) const { out[0] = impl_->lbvhMs; out[1] = (double)impl_->lbvhTris; out[2] = (double)impl_->lbvhNodes; out[3] = (double)impl_->sceneBytes; }
 long long Renderer::getPhotons(double* out6Host, long long cap) { CK(cudaSetDevice(device_)); return impl_->photons.download(out6Host, cap, (cudaStream_t)stream_); }

@@ -2,6 +2,7 @@
 #pragma once
 #include "host_scene.h"
 #include <string>
+#include <vector>
 
 namespace drt {
 
@@ -55,6 +56,7 @@ class Renderer {
   static long long distAbsPixel(int cols, int rows, int world, int rank, int chunkRows, long long compact);   // absolute pixel of a compact slot, -1 beyond the frame
   static void distPhotonRange(long long nCast, int world, int rank, long long out2[2]);
   void renderDistributed(int32_t* argbHostRank0, int32_t* argbDevRank0, int chunkRows, bool reemitPhotons, RenderStats* stats);
+  long long probeFastBvh(int fastIndex, std::vector<FTri>& tris, std::vector<FNode>& nodes, int32_t info[4]);   // resident packed triangles (+ LBVH nodes) of a fast BVH
   void accelInfo(double out[4]) const;                 // LBVH build ms (CUDA events), triangles and nodes it covers, scene bytes in HBM
   int cols() const { return g_.cols; }
   int rows() const { return g_.rows; }

@@ -10,7 +10,8 @@ namespace drt {
 // {M, M^-1, (M^-1)^T} of a reference CTM array (DistRayTracer.java:399); M^T is never read on the hot path.
 struct FXform { double m[16]; double inv[16]; double adj[16]; };
 
-enum PrimType : int32_t { PT_SPHERE = 1, PT_MOVSPHERE = 2, PT_HCYL = 3, PT_CYL = 4, PT_TRI = 5, PT_QUAD = 6, PT_PLANE = 7, PT_BOX = 8 };
+enum PrimType : int32_t { PT_SPHERE = 1, PT_MOVSPHERE = 2, PT_HCYL = 3, PT_CYL = 4, PT_TRI = 5, PT_QUAD = 6, PT_PLANE = 7, PT_BOX = 8,
+                           PT_TORUS = 9, PT_QUADRIC = 10 };      // extension primitives (`extensions on`): the reference only has a torus stub that never hits (myImpObject.java:330-390)
 enum : int32_t { PF_INVERTED = 1 };
 
 // One renderable primitive (mySceneObject subclasses). `data` indexes the double pool `pdata`:

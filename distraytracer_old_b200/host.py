@@ -72,6 +72,7 @@ def load_library():
         "drt_scene_counts": (C.c_int, [vp, C.POINTER(i64)]),
         "drt_build_info": (C.c_int, [vp, C.POINTER(dbl)]),
         "drt_bvh_order": (C.c_int, [vp, i32, vp, vp, i32]),
+        "drt_lbvh_probe": (i64, [vp, i32, i32, vp, vp, vp, vp, vp, i64]),
         "drt_emit_photons": (C.c_int, [vp, C.POINTER(Stats)]),
         "drt_render": (C.c_int, [vp, vp, C.POINTER(Stats)]),
         "drt_render_aov": (C.c_int, [vp, vp, vp, vp, vp, vp, C.POINTER(Stats)]),
@@ -106,7 +107,7 @@ def load_library():
 
 EXPORTS = ["drt_create", "drt_destroy", "drt_last_error", "drt_set_image_loader", "drt_set_texture_dir", "drt_scene_reset",
            "drt_scene_command", "drt_scene_load_cli", "drt_scene_override", "drt_scene_finalize", "drt_scene_reupload",
-           "drt_scene_info", "drt_scene_counts", "drt_build_info", "drt_bvh_order", "drt_accel_info", "drt_emit_photons", "drt_render", "drt_render_aov", "drt_render_device", "drt_render_device_chunks", "drt_save_png",
+           "drt_scene_info", "drt_scene_counts", "drt_build_info", "drt_bvh_order", "drt_lbvh_probe", "drt_accel_info", "drt_emit_photons", "drt_render", "drt_render_aov", "drt_render_device", "drt_render_device_chunks", "drt_save_png",
            "drt_trace_rays", "drt_eval_texture", "drt_dump_bvh", "drt_obj_ctm", "drt_sample_u01", "drt_get_photons",
            "drt_emit_photons_range", "drt_photons_export_device", "drt_photons_build_device", "drt_photon_probe",
            "drt_comm_unique_id", "drt_comm_init", "drt_comm_destroy", "drt_render_distributed",
@@ -127,6 +128,8 @@ class Context:
 
     def __init__(self, device=0, cols=300, rows=300, seed=0x5EED, counters=False, batch_rays=0, texture_dir=TEX_DIR):
         self.L = load_library()
+        if cols <= 0 or rows <= 0:
+            raise DrtError("frame size must be positive (got %d x %d): host buffers are sized from it" % (cols, rows))
         cfg = _Config(device, cols, rows, int(counters), seed, batch_rays)
         h = C.c_void_p()
         rc = self.L.drt_create(C.byref(cfg), C.byref(h))
@@ -235,6 +238,19 @@ class Scene:
         o = (C.c_double * 8)()
         self.ctx._ck(self.L.drt_build_info(self.ctx.h, o))
         return {"parse_ms": o[0], "bvh_order_ms": o[1], "bvh_order_device_ms": o[2], "bvh_shape_ms": o[3], "finalize_ms": o[4], "bvh_device_builds": int(o[5]), "bvh_objects": int(o[6]), "upload_ms": o[7]}
+
+    def lbvh_probe(self, fast_index=0, resident=False):
+        """Packed triangles of a fast BVH (host order, or as resident in HBM) + the GPU-built LBVH nodes (resident, DRT_ACCEL_LBVH mode)."""
+        box = np.zeros(6)
+        n = self.L.drt_lbvh_probe(self.ctx.h, fast_index, 1 if resident else 0, box.ctypes.data, None, None, None, None, 0)
+        if n < 0:
+            return None
+        nn = max(0, (n + 3) // 4 - 1)
+        v, ser, links, boxes = np.zeros((n, 9)), np.zeros(n, dtype=np.int32), np.zeros((nn, 2), dtype=np.int32), np.zeros((nn, 12))
+        r = self.L.drt_lbvh_probe(self.ctx.h, fast_index, 1 if resident else 0, box.ctypes.data, v.ctypes.data, ser.ctypes.data, links.ctypes.data, boxes.ctypes.data, n)
+        if r < 0:
+            self.ctx._ck(int(r))
+        return {"box": box, "verts": v, "serial": ser, "links": links, "boxes": boxes}
 
     def accel_info(self):
         o = (C.c_double * 4)()

@@ -71,6 +71,13 @@ int drt_build_info(drt_ctx* ctx, double* out8);
    keys3n = [3][n]; ord[n] = leaves left to right, each in the order the reference's leaf list holds them, the object dropped at the root
     last.  on_device != 0: the device builder (segmented radix sorts), else the host recursion -- the two must agree bit for bit. */
 int drt_bvh_order(drt_ctx* ctx, int32_t n, const double* keys3n, int32_t* ord, int32_t on_device);
+/* parity probe for the fast BVHs (north star subsystem 2: "Morton/BVH ordering must be bit-exact"): packed triangles of fast BVH number
+   fast_index (scene order) -- 9 vertex coordinates + primitive serial each -- in the order of the host flattener (which = 0: the reference
+   tree's DFS order = the input order of the Morton sort) or as resident in HBM (which = 1: after the device LBVH build in DRT_ACCEL_LBVH mode),
+   the BVH's root box, and (which = 1, LBVH mode) the built nodes: child links (>= 0 node, < 0: -(1 + leaf), leaf j = resident triangles
+   4j..4j+3) and both child boxes.  Returns the triangle count (-1: no such BVH); arrays are filled only when cap_tris >= count.
+   Buffers: verts9[9n], prim_serial[n], links2[2(ceil(n/4)-1)], boxes12[12(ceil(n/4)-1)]; any may be NULL. */
+int64_t drt_lbvh_probe(drt_ctx* ctx, int32_t fast_index, int32_t which, double* box6, double* verts9, int32_t* prim_serial, int32_t* links2, double* boxes12, int64_t cap_tris);
 int drt_scene_counts(drt_ctx* ctx, int64_t* out8);               /* flattener products of the fast paths: packed triangles, fast BVHs, packed top-level triangles, triangles in fast BVHs, children, pdata doubles, 0, 0 */
 int drt_scene_info(drt_ctx* ctx, int32_t* out16);                /* cols, rows, spp, top objects, lights, prims, instances, photon kind, shaders, nodes, xforms, lists, ... */
 

@@ -20,6 +20,10 @@ final class DrtNative implements AutoCloseable {
   private static final MethodHandle TEXDIR   = h("drt_set_texture_dir",FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
   private static final MethodHandle FINALIZE = h("drt_scene_finalize", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
   private static final MethodHandle RENDER   = h("drt_render",         FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+  // multi-GPU inside the library (include/drt.h: drt_comm_unique_id / drt_comm_init / drt_render_distributed), one DrtNative per GPU
+  private static final MethodHandle COMM_ID   = h("drt_comm_unique_id",     FunctionDescriptor.of(JAVA_INT, ADDRESS));
+  private static final MethodHandle COMM_INIT = h("drt_comm_init",          FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT));
+  private static final MethodHandle RENDER_D  = h("drt_render_distributed", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
 
   private final Arena arena = Arena.ofConfined();
   private final MemorySegment ctx;
@@ -47,6 +51,18 @@ final class DrtNative implements AutoCloseable {
       MemorySegment px = a.allocate(JAVA_INT, (long) cols * rows);
       check((int) RENDER.invoke(ctx, px, MemorySegment.NULL));
       return px.toArray(JAVA_INT);
+    }
+  }
+  /** rank 0: the 128-byte communicator id the host ships to the other ranks by any transport */
+  static byte[] commUniqueId() throws Throwable { try (Arena a = Arena.ofConfined()) { MemorySegment id = a.allocate(128); int rc = (int) COMM_ID.invoke(id); if (rc != 0) throw new IllegalStateException("drt_comm_unique_id " + rc); return id.toArray(JAVA_BYTE); } }
+  void commInit(byte[] id128, int world, int rank) throws Throwable { try (Arena a = Arena.ofConfined()) { check((int) COMM_INIT.invoke(ctx, a.allocateFrom(JAVA_BYTE, id128), world, rank)); } }
+  /** collective: every rank renders its interleaved 8-row chunks; rank 0 gets the assembled frame, the others null */
+  int[] renderDistributed(int accelMode, int rank) throws Throwable {
+    check((int) FINALIZE.invoke(ctx, accelMode));
+    try (Arena a = Arena.ofConfined()) {
+      MemorySegment px = rank == 0 ? a.allocate(JAVA_INT, (long) cols * rows) : MemorySegment.NULL;
+      check((int) RENDER_D.invoke(ctx, px, MemorySegment.NULL, 8, 1, MemorySegment.NULL));
+      return rank == 0 ? px.toArray(JAVA_INT) : null;
     }
   }
   @Override public void close() { try { DESTROY.invoke(ctx); } catch (Throwable t) { } arena.close(); }

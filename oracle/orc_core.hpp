@@ -107,7 +107,7 @@ struct BBox {                                                     // myGeomBase.
   }
 };
 
-enum GType { G_NONE, G_SPHERE, G_MOVSPHERE, G_HCYL, G_CYL, G_TRI, G_QUAD, G_PLANE, G_BOX, G_INSTANCE, G_LIST, G_BVH, G_POINTLIGHT, G_SPOTLIGHT, G_DISKLIGHT };
+enum GType { G_NONE, G_SPHERE, G_MOVSPHERE, G_HCYL, G_CYL, G_TRI, G_QUAD, G_PLANE, G_BOX, G_INSTANCE, G_LIST, G_BVH, G_POINTLIGHT, G_SPOTLIGHT, G_DISKLIGHT, G_TORUS, G_QUADRIC };
 
 struct Geom {                                                     // myGeomBase.java:10-87
   Scene* scene; int ID; GType type = G_NONE;

@@ -41,6 +41,7 @@ struct Scene {
   Sphere* mySkyDome = nullptr; const Image* skyTex = nullptr;
   int numLights = 0, objCount = 0, numNonLights = 0;
   // flags (myScene.java:72-98)
+  bool extensions = false;        // `extensions on` (orc_ext.hpp)
   bool simpleRefr = false, hasDpthOfFld = false, addToTmpList = false, glblTxtrdBkg = false, glblRefine = false,
        glblTxtrdTop = false, glblTxtrdBtm = false, usePhotonMap = false, isCausticPhtn = false, isPhtnMapRndrd = false;
   KDTree* photonTree = nullptr; int numPhotons = 0, kNhood = 0; float ph_max_near_dist = 0;
@@ -867,6 +868,9 @@ struct Tok {
 };
 inline std::string lower(std::string s) { for (auto& c : s) c = (char)tolower(c); return s; }
 
+}  // namespace orc
+#include "orc_ext.hpp"
+namespace orc {
 inline void Scene::readPrimData(const std::vector<std::string>& tv) {           // myScene.java:447-521
   Tok k{tv}; Geom* tmp = nullptr; const std::string& c = tv[0];
   if (c == "box") {
@@ -884,6 +888,14 @@ inline void Scene::readPrimData(const std::vector<std::string>& tv) {           
   else if (c == "moving_sphere") tmp = new MovingSphere(this, k.d(1), k.d(2), k.d(3), k.d(4), k.d(5), k.d(6), k.d(7));
   else if (c == "sphereIn") { double r = k.d(1); tmp = new Sphere(this, r, r, r, k.d(2), k.d(3), k.d(4)); tmp->inverted = true; }
   else if (c == "ellipsoid") tmp = new Sphere(this, k.d(1), k.d(2), k.d(3), k.d(4), k.d(5), k.d(6));
+  else if (c == "torus") { const bool six = tv.size() >= 7; tmp = new Torus(this, k.d(1), k.d(2), k.d(six ? 4 : 3), k.d(six ? 5 : 4), k.d(six ? 6 : 5)); }      // extension, see orc_ext.hpp
+  else if (c == "quadric") {
+    double coef[10], bx[6] = {-100000, -100000, -100000, 100000, 100000, 100000};
+    for (int i = 0; i < 10; ++i) coef[i] = k.d(1 + i);
+    if (tv.size() >= 17) for (int i = 0; i < 6; ++i) bx[i] = k.d(11 + i);
+    for (int i = 0; i < 3; ++i) if (bx[i] > bx[3 + i]) std::swap(bx[i], bx[3 + i]);
+    tmp = new Quadric(this, coef, bx);
+  }
   else return;
   tmp->primSerial = primSerialCnt++;
   tmp->shdr = getCurShader(); addObjectToScene(tmp);
@@ -1009,6 +1021,8 @@ inline void Scene::readRTFile(const std::string& fileName, bool isMain) {
       vertType = "triangle"; myVertCount = 0;
     }
     else if (c == "box" || c == "plane" || c == "cyl" || c == "cylinder" || c == "hollow_cylinder" || c == "sphere" || c == "moving_sphere" || c == "sphereIn" || c == "ellipsoid") readPrimData(k.t);
+    else if (c == "extensions") { bool on = true; try { std::string v = k.s(1); for (auto& ch : v) ch = (char)tolower(ch); on = v != "off"; } catch (TokErr&) {} extensions = on; }
+    else if ((c == "torus" || c == "quadric") && extensions) readPrimData(k.t);
     else if (c == "push") gtPushMatrix();
     else if (c == "pop") gtPopMatrix();
     else if (c == "rotate") gtRotate(k.d(1), k.d(2), k.d(3), k.d(4));

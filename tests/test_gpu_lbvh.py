@@ -122,3 +122,23 @@ def test_synthetic_scaling_scenes_sampled_rays_match_oracle(drt, orc, gpu_ctx_fa
         assert (gi != oi).any(axis=1).sum() <= 2, (kind, accel, (gi != oi).any(axis=1).sum())
         same = (gi == oi).all(axis=1)
         assert np.array_equal(gt[same], ot[same]), (kind, accel)
+
+
+@pytest.mark.parametrize("name", ["p3_t09", "gen/soup_65536"])
+def test_lbvh_morton_order_and_tree_equal_the_cpu_restatement(drt, gpu_ctx_factory, name):
+    """North star: "Morton/BVH ordering must be bit-exact".  The device build (k_lbvh_morton, radix sort, k_lbvh_hierarchy, k_lbvh_refit) against
+    oracle/lbvh_oracle.py: resident triangle order, every child link and every node box."""
+    from oracle import lbvh_oracle
+    if name.startswith("gen/") and not os.path.exists(os.path.join(ROOT, "scenes", name + ".cli")):
+        import subprocess, sys
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_synth.py"), "soup", "65536"])
+    ctx = gpu_ctx_factory(64, 64)
+    s = drt.Scene.from_cli(ctx, name + ".cli", accel=drt.ACCEL_LBVH)
+    host, dev = s.lbvh_probe(0, resident=False), s.lbvh_probe(0, resident=True)
+    assert len(host["verts"]) == len(dev["verts"]) > 1000 and len(dev["links"]) == (len(dev["verts"]) + 3) // 4 - 1
+    order, links, boxes = lbvh_oracle.build(host["verts"], host["box"])
+    assert np.array_equal(host["serial"][order], dev["serial"])                 # Morton order, ties in input order
+    assert np.array_equal(host["verts"][order], dev["verts"])
+    assert np.array_equal(links, dev["links"])                                  # Karras hierarchy
+    assert np.array_equal(boxes, dev["boxes"])                                  # refit boxes, bit for bit
+    ctx.close()
