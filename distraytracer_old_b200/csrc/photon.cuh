@@ -563,7 +563,7 @@ __device__ inline bool phLaneTiers(const DScene& S, bool needs, D3 loc, PhLaneSh
       }
       sum[0] = s0; sum[1] = s1; sum[2] = s2; dmax2 = mx; needs = false; if (path) *path = 1;
     }
-    if (needs && cnt <= DRT_PH_LANE_MAX) {                                 // tier 2
+    if (needs && cnt <= DRT_PH_LANE_MAX) {                                 // tier 2 (an FP32 pre-test form of this tier was measured and lost: profiles/r2_tuning.md)
       // pass 1 bins d^2 into the lane's histogram (bin index monotone in d^2) and finds the bin of the k-th neighbour; pass 2 sums the bins
       // below it and resolves the boundary bin exactly from a register list sorted by (d^2, index). A boundary bin with more than 8 photons
       // hands the query to the warp-cooperative tier.

@@ -473,7 +473,7 @@ struct Renderer::Impl {
   cudaEvent_t pev(size_t k) { while (evPool.size() <= k) { cudaEvent_t e; CK(cudaEventCreate(&e)); evPool.push_back(e); } return evPool[k]; }
   DBuf<int32_t> oArgb, oPrim, oInst; DBuf<double> oRgb, oT;
   cudaEvent_t ev[8];
-  PhotonMap photons;
+  PhotonMap photons; PhotonMap::Scratch xCnt, xMine, xAll;      // photon record exchange of drt_render_distributed
   size_t sceneBytes = 0;
   float lbvhMs = 0; long long lbvhTris = 0, lbvhNodes = 0;
   std::vector<FBvh> bvhsUploaded;                // host copy of the FBvh array as uploaded (fastRoot points at the LBVH nodes in DRT_ACCEL_LBVH mode)
@@ -499,7 +499,7 @@ Renderer::~Renderer() {
   impl_->rays[0].release(); impl_->rays[1].release(); impl_->hits.release(); impl_->hits0.release(); impl_->surf.release(); impl_->nodes.release();
   impl_->oArgb.release(); impl_->oPrim.release(); impl_->oInst.release(); impl_->oRgb.release(); impl_->oT.release();
   impl_->deferT.release(); impl_->deferL.release(); for (auto& e : impl_->evPool) cudaEventDestroy(e);
-  impl_->photons.release();
+  impl_->photons.release(); impl_->xCnt.release(); impl_->xMine.release(); impl_->xAll.release();
   cudaFree(impl_->ctr); cudaFreeHost(impl_->ctrHost);
   for (auto& e : impl_->ev) cudaEventDestroy(e);
   cudaStreamDestroy((cudaStream_t)stream_); delete impl_;
@@ -516,7 +516,9 @@ void Renderer::upload(const HostScene& hs, bool sameScene) {
   CK(cudaSetDevice(device_)); cudaStream_t st = (cudaStream_t)stream_;
   CK(cudaStreamSynchronize(st));
   // device-side nesting limits (see dev_isect.cuh): accel children are primitives or instances; an instanced accel holds primitives
+  std::vector<char> seenBase[2] = {std::vector<char>(hs.lists.size(), 0), std::vector<char>(hs.bvhs.size(), 0)};      // 21 845 instances of one mesh: check the mesh once
   for (const FInstance& in : hs.instances) if (in.baseKind == OK_LIST || in.baseKind == OK_BVH) {
+    { std::vector<char>& seen = seenBase[in.baseKind == OK_BVH ? 1 : 0]; if (in.baseIdx >= 0 && (size_t)in.baseIdx < seen.size()) { if (seen[in.baseIdx]) continue; seen[in.baseIdx] = 1; } }
     auto checkList = [&](const FList& L) { for (int i = 0; i < L.childCount; ++i) { const FObjRef& c = hs.children[L.childStart + i];
       if (c.kind == OK_INSTANCE && hs.instances[c.idx].baseKind != OK_PRIM) throw std::runtime_error("instances nested deeper than TLAS->instance->BLAS are not supported on the device"); } };
     if (in.baseKind == OK_LIST) checkList(hs.lists[in.baseIdx]);
@@ -864,18 +866,19 @@ void Renderer::renderDistributed(int32_t* argbHostRank0, int32_t* argbDevRank0, 
     long long pr[2]; distPhotonRange(g_.numPhotonsCast, world, rank, pr); const long long i0 = pr[0], i1 = pr[1];
     devErrorReset(st); I.photons.emitRange(I.ds, i0, i1, I.ctr, I.ctrHost, st); devErrorCheck(st);
     if (world > 1) {
-      unsigned long long* cnt = nullptr; CK(cudaMalloc(&cnt, sizeof(unsigned long long) * (world + 1)));
+      // (exchange buffers are grow-only members: a cudaMalloc / cudaFree pair per frame costs tens to hundreds of ms on this driver)
+      unsigned long long* cnt = I.xCnt.get<unsigned long long>((size_t)world + 1);
       k_store_u64<<<1, 1, 0, st>>>(cnt + world, I.photons.count);
       NK(nccl().AllGather(cnt + world, cnt, 1, ncclUint64, (ncclComm_t)comm_, st));
-      std::vector<unsigned long long> counts(world); CK(cudaMemcpyAsync(counts.data(), cnt, sizeof(unsigned long long) * world, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); cudaFree(cnt);
+      std::vector<unsigned long long> counts(world); CK(cudaMemcpyAsync(counts.data(), cnt, sizeof(unsigned long long) * world, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
       unsigned long long mx = 1, total = 0, segs = I.photons.segments; for (auto c : counts) { mx = std::max(mx, c); total += c; }
-      PhotonRec *mine = nullptr, *all = nullptr; CK(cudaMalloc(&mine, mx * sizeof(PhotonRec))); CK(cudaMalloc(&all, mx * world * sizeof(PhotonRec)));
+      PhotonRec* mine = I.xMine.get<PhotonRec>((size_t)mx); PhotonRec* all = I.xAll.get<PhotonRec>((size_t)mx * world);
       CK(cudaMemsetAsync(mine, 0, mx * sizeof(PhotonRec), st));
       if (I.photons.count) CK(cudaMemcpyAsync(mine, I.photons.rec, I.photons.count * sizeof(PhotonRec), cudaMemcpyDeviceToDevice, st));
       NK(nccl().AllGather(mine, all, mx * sizeof(PhotonRec), ncclChar, (ncclComm_t)comm_, st));
       I.photons.built = false; I.photons.emitted = true; I.photons.count = 0; I.photons.ensureRec((size_t)total, st);
       unsigned long long at = 0; for (int r = 0; r < world; ++r) { if (counts[r]) CK(cudaMemcpyAsync(I.photons.rec + at, all + (size_t)r * mx, counts[r] * sizeof(PhotonRec), cudaMemcpyDeviceToDevice, st)); at += counts[r]; }
-      I.photons.count = total; I.photons.segments = segs; CK(cudaStreamSynchronize(st)); cudaFree(mine); cudaFree(all);
+      I.photons.count = total; I.photons.segments = segs; CK(cudaStreamSynchronize(st));
     }
     I.photons.buildGrid(I.ds, st);
     CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st)); CK(cudaEventElapsedTime(&msPhoton, e0, e1)); photonLaunches = g_kernelLaunches - l0;

@@ -18,7 +18,7 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_
 timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; tail -c 1500 $OUT/${TAG}_bench.json
 PROF="python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e"
 timeout 600 $PROF > $OUT/${TAG}_plain.log 2>&1 && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/${TAG}_launches.csv $PROF > $OUT/${TAG}_ncu_launches.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/${TAG}_launches.csv $PROF > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"
 PROF2="python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --res 1920x1080 --spp 4"
 timeout 600 $PROF2 > $OUT/${TAG}_plain2.log 2>&1 && \
