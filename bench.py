@@ -350,7 +350,7 @@ def main():
         line = {"metric": METRIC, "value": round(value, 3), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": make_config(w, world, args.accel, has_photons),
-                "frame_ms": round(ms_per_step, 3), "frame_crc32": frame_crc, "rays_per_frame": rays, "ray_types_per_frame": ray_types, "accel_info": scene.accel_info(),
+                "frame_ms": round(ms_per_step, 3), "frame_crc32": frame_crc, "rays_per_frame": rays, "ray_types_per_frame": ray_types, "accel_info": scene.accel_info(), "build_info": {k: (round(v, 2) if isinstance(v, float) else v) for k, v in scene.build_info().items()},
                 "stages_ms_rank0_last_step": {k: round(v, 3) for k, v in stage.items()}, "gpu_launches": launches, "host_syncs_per_frame": int(st.host_syncs), "rays_deferred_to_generic_kernels": int(st.rays_deferred),
                 "clocks": clocks, "e2e": e2e, "sample": sample, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)

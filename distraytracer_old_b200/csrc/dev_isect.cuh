@@ -104,9 +104,10 @@ __device__ __forceinline__ int boxQuick(const double* __restrict__ mn, const dou
   const double tnx = sx ? ax1 : ax2, tfx = sx ? ax2 : ax1, tny = sy ? ay1 : ay2, tfy = sy ? ay2 : ay1, tnz = sz ? az1 : az2, tfz = sz ? az2 : az1;
   double far_ = tfx; if (tfy < far_) far_ = tfy; if (tfz < far_) far_ = tfz;
   double near_ = tnx; if (tny > near_) near_ = tny; if (tnz > near_) near_ = tnz;
+  nearApprox = near_;                       // defined on every return path (callers scale it before looking at the verdict)
   if (!(fabs(near_) > 1e-290) || !(fabs(far_) < 1e290) || !(fabs(near_) < 1e290)) return -1;
   const double tol = 1e-14 * (fabs(far_) + fabs(near_)), gap = far_ - near_;
-  if (gap > tol) { nearApprox = near_; return near_ > 0 ? 1 : 0; }
+  if (gap > tol) return near_ > 0 ? 1 : 0;
   return (-gap > tol) ? 0 : -1;
 }
 // box accepted?  te = conservative LOWER bound of the entry t (exact when the quick path could not decide)
@@ -334,8 +335,8 @@ __device__ __forceinline__ bool boxTestStd(const double* mn, const double* mx, c
 #ifndef DRT_LEAN
 #define DRT_LEAN 1
 #endif
-// The traversal bodies are force-inlined: as __noinline__ functions (one shared copy) they ran at the same speed but one build computed wrong
-// closest hits in unrelated, never-executed-together paths of the same kernel (found by tools/dbg_modes2.py, not explained) -- see DESIGN.md.
+// The traversal bodies are force-inlined in the lean kernels so that ray and hit records stay in registers; -DDRT_LEAN_INLINE=__noinline__ builds the
+// outlined form, which passes the same equivalence tests (`__noinline__` note).
 #ifndef DRT_LEAN_INLINE
 #define DRT_LEAN_INLINE __forceinline__
 #endif
