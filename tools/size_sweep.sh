@@ -2,7 +2,7 @@
 # Synthetic size sweep of SURVEY 8(d) at N = 1 (soups 2^18 / 2^22, replicated-bunny grids k = 8 / 16; 2^16, 2^20 and k = 4 are in the scaling study):
 #   gpurun -- 'bash tools/size_sweep.sh'   -> gpurun_out/r2_sizes.jsonl (bench lines incl. build_info: .cli interpretation, device ordering, host shape)
 # Soups stop at 2^22 here: the drop-in boundary is the reference's TEXT scene format, 5 lines per triangle -- 2^24 triangles are 84 M lines / 3 GB of
-# .cli and ~2 min of interpretation per rank before the first ray; the device-side ordering itself was measured to 2^24 objects (r2b_refbvh_time.jsonl).
+# .cli and most of a minute of interpretation per rank before the first ray; the device-side ordering itself was measured to 2^24 objects (r2b_refbvh_time.jsonl).
 OUT=gpurun_out/r2_sizes.jsonl
 mkdir -p gpurun_out; : > $OUT
 python __graft_entry__.py > gpurun_out/r2_sizes_build.log 2>&1
