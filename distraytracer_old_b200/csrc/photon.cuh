@@ -324,26 +324,6 @@ __device__ inline bool phWarpGather(const DScene& S, D3 p, double r2, bool needA
   return true;
 }
 
-// The candidate ranges of one query, as contiguous photon index ranges: G(a, b) per range.  Two shapes of candidate set, as in phWarpGather.
-template <class G_>
-__device__ __forceinline__ void phForRanges(const DScene& S, int fineHalf, const int lo[3], const int hi[3], G_&& G) {
-  if (fineHalf < 0) {
-    for (int cz = lo[2]; cz <= hi[2]; ++cz) for (int cy = lo[1]; cy <= hi[1]; ++cy) {
-      const uint32_t row = ((uint32_t)cz * S.gridDim[1] + (uint32_t)cy) * S.gridDim[0];
-      G(S.cellStart[(size_t)(row + lo[0]) << 6], S.cellStart[(size_t)(row + hi[0] + 1) << 6]);
-    }
-  } else {
-    const int z0 = lo[2], z1 = hi[2], y0 = lo[1], y1 = hi[1], x0 = lo[0], x1 = hi[0];
-    for (int fz = z0; fz <= z1; ++fz) for (int fy = y0; fy <= y1; ++fy) {
-      const uint32_t crow = ((uint32_t)(fz >> 2) * S.gridDim[1] + (uint32_t)(fy >> 2)) * S.gridDim[0], sub = ((uint32_t)(fz & 3) << 4) | ((uint32_t)(fy & 3) << 2);
-      for (int fx = x0; fx <= x1; ) {
-        const int runEnd = min(x1, fx | 3); const size_t k0 = ((size_t)(crow + (uint32_t)(fx >> 2)) << 6) | sub | (uint32_t)(fx & 3);
-        G(S.cellStart[k0], S.cellStart[k0 + (size_t)(runEnd - fx) + 1]);
-        fx = runEnd + 1;
-      }
-    }
-  }
-}
 // FP32 pre-test form of phWarpGather: the same exact result from ONE histogram pass and one collection pass, both in FP32.
 // The FP64 selection above re-reads every candidate's 32-byte position and re-forms d^2 in FP64 for every radix level (2-3 scans of ~11 FP64-pipe
 // operations per candidate: the half-rate FP64 pipe is what bounds dense maps).  Here d^2 is formed in FP32 from a float4 mirror of the positions;
