@@ -172,3 +172,33 @@ def test_unknown_accel_mode_is_rejected(drt):
         s.finalize(7)
     s.finalize(drt.ACCEL_LBVH)          # host-only context: flattening succeeds, nothing is uploaded
     ctx.close()
+
+
+def test_vertex_fast_path_keeps_the_token_rules(drt):
+    """`vertex` lines are parsed in place (no token list); the rules must stay those of PApplet.splitTokens(line, " ") + Java number parsing as the
+    general path applies them: any number of blanks, trailing tokens ignored, f / d suffixes accepted, a missing or malformed number is an error
+    only when the vertex would be used (inside begin ... end, before the polygon is full)."""
+    ctx = drt.Context(device=-1)
+
+    def verts(lines):
+        sc = drt.Scene(ctx)
+        for l in ["diffuse .8 .8 .8 .1 .1 .1", "begin_list"] + (["begin"] + lines + ["end"]) * 8 + ["end_accel", "write x.png"]:
+            sc.command(l)
+        sc.finalize()
+        p = sc.lbvh_probe(0)                      # packed triangles of the mesh (the reference's tree drops one of the eight, SURVEY Q2)
+        assert sc.info()["prims"] == 8 and p is not None and len(p["verts"]) == 7
+        return p["verts"]
+
+    va = verts(["vertex 0 0.25 -5", "vertex 1.5 0 -5", "vertex 0 2 -5"])
+    vb = verts(["   vertex   0   0.25f  -5d   trailing tokens", "vertex 1.5e0 +0 -5.0", "vertex 0 2 -.5e1", "vertex 9 9 9"])     # the fourth vertex of a triangle is ignored
+    assert np.array_equal(va, vb) and np.array_equal(va[0], [0, 0.25, -5, 1.5, 0, -5, 0, 2, -5])
+    c = drt.Scene(ctx)
+    c.command("vertex nonsense here")             # outside begin ... end the reference never reads the numbers
+    c.command("begin")
+    with pytest.raises(drt.DrtError, match="malformed"):
+        c.command("vertex 1 2")
+    with pytest.raises(drt.DrtError, match="malformed"):
+        c.command("vertex 1 2 3x")
+    with pytest.raises(drt.DrtError, match="malformed"):
+        c.command("vertex 1 two 3")
+    ctx.close()
