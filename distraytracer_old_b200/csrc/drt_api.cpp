@@ -100,7 +100,7 @@ int64_t drt_lbvh_probe(drt_ctx* ctx, int32_t fast_index, int32_t which, double* 
       else n = ctx->renderer->probeFastBvh(fast_index, tris, nodes, info);
       break;
     }
-    if (n < 0) return -1;
+    if (n < 0) return DRT_ERR_BAD_ARG;            // no such fast BVH
     for (long long i = 0; i < n && i < cap_tris; ++i) { if (verts9) std::memcpy(verts9 + 9 * i, tris[i].v, 72); if (prim_serial) prim_serial[i] = hs.prims[tris[i].prim].serial; }
     // links: >= 0 inner node (relative to the BVH's first LBVH node), < 0: -(1 + leaf number), leaf j = triangles 4j .. 4j+3 of the resident order
     if (n <= cap_tris) for (size_t i = 0; i < nodes.size(); ++i) { const FNode& N = nodes[i];

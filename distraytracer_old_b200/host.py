@@ -243,8 +243,10 @@ class Scene:
         """Packed triangles of a fast BVH (host order, or as resident in HBM) + the GPU-built LBVH nodes (resident, DRT_ACCEL_LBVH mode)."""
         box = np.zeros(6)
         n = self.L.drt_lbvh_probe(self.ctx.h, fast_index, 1 if resident else 0, box.ctypes.data, None, None, None, None, 0)
-        if n < 0:
+        if n == -2:                          # DRT_ERR_BAD_ARG: no such fast BVH
             return None
+        if n < 0:
+            self.ctx._ck(int(n))
         nn = max(0, (n + 3) // 4 - 1)
         v, ser, links, boxes = np.zeros((n, 9)), np.zeros(n, dtype=np.int32), np.zeros((nn, 2), dtype=np.int32), np.zeros((nn, 12))
         r = self.L.drt_lbvh_probe(self.ctx.h, fast_index, 1 if resident else 0, box.ctypes.data, v.ctypes.data, ser.ctypes.data, links.ctypes.data, boxes.ctypes.data, n)

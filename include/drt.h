@@ -75,7 +75,8 @@ int drt_bvh_order(drt_ctx* ctx, int32_t n, const double* keys3n, int32_t* ord, i
    fast_index (scene order) -- 9 vertex coordinates + primitive serial each -- in the order of the host flattener (which = 0: the reference
    tree's DFS order = the input order of the Morton sort) or as resident in HBM (which = 1: after the device LBVH build in DRT_ACCEL_LBVH mode),
    the BVH's root box, and (which = 1, LBVH mode) the built nodes: child links (>= 0 node, < 0: -(1 + leaf), leaf j = resident triangles
-   4j..4j+3) and both child boxes.  Returns the triangle count (-1: no such BVH); arrays are filled only when cap_tris >= count.
+   4j..4j+3) and both child boxes.  Returns the triangle count (DRT_ERR_BAD_ARG: no such BVH; DRT_ERR_NO_DEVICE: which = 1 on a host-only context); arrays are filled only
+   when cap_tris >= count.
    Buffers: verts9[9n], prim_serial[n], links2[2(ceil(n/4)-1)], boxes12[12(ceil(n/4)-1)]; any may be NULL. */
 int64_t drt_lbvh_probe(drt_ctx* ctx, int32_t fast_index, int32_t which, double* box6, double* verts9, int32_t* prim_serial, int32_t* links2, double* boxes12, int64_t cap_tris);
 int drt_scene_counts(drt_ctx* ctx, int64_t* out8);               /* flattener products of the fast paths: packed triangles, fast BVHs, packed top-level triangles, triangles in fast BVHs, children, pdata doubles, 0, 0 */

@@ -202,3 +202,22 @@ def test_vertex_fast_path_keeps_the_token_rules(drt):
     with pytest.raises(drt.DrtError, match="malformed"):
         c.command("vertex 1 two 3")
     ctx.close()
+
+
+def test_build_probes_on_a_host_only_context(drt):
+    """drt_build_info / drt_bvh_order / drt_lbvh_probe without a device: the host halves work, the device halves fail loudly (no CPU fallback)."""
+    ctx = drt.Context(device=-1)
+    s = drt.Scene.from_cli(ctx, "p3_t08.cli")
+    b = s.build_info()
+    assert b["bvh_objects"] == 966 and b["bvh_device_builds"] == 0 and b["parse_ms"] > 0 and b["upload_ms"] == 0
+    p = s.lbvh_probe(0, resident=False)
+    assert p is not None and len(p["verts"]) == 965 and len(p["links"]) == (965 + 3) // 4 - 1      # one object dropped at the root (Q2)
+    assert s.lbvh_probe(5, resident=False) is None
+    with pytest.raises(drt.DrtError):
+        s.lbvh_probe(0, resident=True)
+    keys = np.random.default_rng(1).normal(size=(100, 3))
+    assert sorted(ctx.bvh_order(keys, on_device=False)) == list(range(100))
+    assert len(ctx.bvh_order(np.zeros((0, 3)), on_device=False)) == 0
+    with pytest.raises(drt.DrtError):
+        ctx.bvh_order(keys, on_device=True)
+    ctx.close()
