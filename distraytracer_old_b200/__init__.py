@@ -14,4 +14,4 @@ interface for the path:
 
 There is no CPU fallback: without the built library or without a CUDA device every render call raises.
 """
-from .host import Context, Scene, RTFileReader, DrtError, lib_path, load_library, SCENES_DIR, ACCEL_REFERENCE, ACCEL_REFERENCE_FAST, ACCEL_LBVH  # noqa: F401
+from .host import Context, Scene, RTFileReader, DrtError, lib_path, load_library, refine_steps, refine_pass, SCENES_DIR, ACCEL_REFERENCE, ACCEL_REFERENCE_FAST, ACCEL_LBVH  # noqa: F401

@@ -1,7 +1,9 @@
 // C ABI (include/drt.h) over the host interpreter/flattener and the device renderer.
 #include "../../include/drt.h"
 #include "renderer.h"
+#include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -151,6 +153,23 @@ int drt_render_distributed(drt_ctx* ctx, int32_t* argb_host, int32_t* argb_dev, 
 int64_t drt_dist_rank_pixels(int32_t cols, int32_t rows, int32_t world, int32_t rank, int32_t chunk_rows) { if (cols < 1 || rows < 1 || world < 1 || rank < 0 || rank >= world || chunk_rows < 1) return DRT_ERR_BAD_ARG; return Renderer::distRankPixels(cols, rows, world, rank, chunk_rows); }
 int64_t drt_dist_abs_pixel(int32_t cols, int32_t rows, int32_t world, int32_t rank, int32_t chunk_rows, int64_t compact) { if (cols < 1 || rows < 1 || world < 1 || rank < 0 || rank >= world || chunk_rows < 1 || compact < 0) return DRT_ERR_BAD_ARG; return Renderer::distAbsPixel(cols, rows, world, rank, chunk_rows, compact); }
 int drt_dist_photon_range(int64_t n, int32_t world, int32_t rank, int64_t* out2) { if (!out2 || world < 1 || rank < 0 || rank >= world || n < 0) return DRT_ERR_BAD_ARG; long long o[2]; Renderer::distPhotonRange(n, world, rank, o); out2[0] = o[0]; out2[1] = o[1]; return DRT_OK; }
+
+int drt_scene_refine(drt_ctx* ctx) { if (!ctx) return DRT_ERR_BAD_ARG; return ctx->scene->refine ? 1 : 0; }
+int32_t drt_refine_steps(int32_t cols, int32_t rows, int32_t* steps16) {          // myScene.setRefine (:796-803)
+  if (cols < 1 || rows < 1) return 0;
+  const int refIDX = (int)(std::log10(.5 * (cols + rows) / 16.0) / std::log10(2.0));
+  if (refIDX < 0 || refIDX > 15) return 0;                                         // `new int[refIDX + 1]` / pow2[] of the reference
+  for (int i = refIDX; i >= 0; --i) if (steps16) steps16[refIDX - i] = 1 << i;
+  return refIDX + 1;
+}
+int drt_refine_pass(const int32_t* full, int32_t cols, int32_t rows, int32_t step, int32_t* out) {     // the pass loop of draw() + writePxlSpan
+  if (!full || !out || cols < 1 || rows < 1 || step < 1) return DRT_ERR_BAD_ARG;
+  for (int row = 0; row < rows; row += step) for (int col = 0; col < cols; col += step) {
+    const int32_t c = full[(size_t)row * cols + col]; const int rEnd = std::min(row + step, rows), cEnd = std::min(col + step, cols);
+    for (int r = row; r < rEnd; ++r) for (int q = col; q < cEnd; ++q) out[(size_t)r * cols + q] = c;
+  }
+  return DRT_OK;
+}
 
 // PNG (8-bit RGB, zlib deflate) -- PImage.save of an RGB image
 int drt_save_png(const char* path, const int32_t* argb, int32_t cols, int32_t rows) {

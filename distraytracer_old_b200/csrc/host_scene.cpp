@@ -508,7 +508,8 @@ void HostScene::command(const std::string& line) {
     else if (c == "lens") { g.lensRadius = k.num(1); g.focalD = k.num(2); g.hasDof = 1; }
     else if (c == "write") { saveName = k.str(1); sawWrite = true; }
     else if (c == "read") readFile(k.str(1), false);
-    else if (c == "reset_timer" || c == "print_timer" || c == "refine") { if (c == "refine") (void)k.str(1); }
+    else if (c == "reset_timer" || c == "print_timer") {}
+    else if (c == "refine") refine = lowered(k.str(1)) == "on";                 // setRefine, myScene.java:796-803 (the previews are made by drt_refine_pass)
     else if (c == "rays_per_pixel") { int r = k.integer(1); curSpp_ = r; g.spp = r; }
     else if (c == "antialias") { int r = k.integer(1) * k.integer(2); curSpp_ = r; g.spp = r; }
     else if (c == "background") {

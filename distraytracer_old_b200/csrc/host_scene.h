@@ -69,6 +69,7 @@ class HostScene {
   std::vector<std::string> warnings;
   std::string saveName;
   bool sawWrite = false;
+  bool refine = false;                // `refine on` (myScene.setRefine): the host shows the progressive previews of drt_refine_pass
   // ---- introspection used by tests (BVH order KAT)
   void dumpBvh(int topIdx, std::vector<int32_t>& out, double box[6]) const;
 

@@ -72,6 +72,9 @@ def load_library():
         "drt_scene_counts": (C.c_int, [vp, C.POINTER(i64)]),
         "drt_build_info": (C.c_int, [vp, C.POINTER(dbl)]),
         "drt_bvh_order": (C.c_int, [vp, i32, vp, vp, i32]),
+        "drt_scene_refine": (C.c_int, [vp]),
+        "drt_refine_steps": (i32, [i32, i32, C.POINTER(i32)]),
+        "drt_refine_pass": (C.c_int, [vp, i32, i32, i32, vp]),
         "drt_lbvh_probe": (i64, [vp, i32, i32, vp, vp, vp, vp, vp, i64]),
         "drt_emit_photons": (C.c_int, [vp, C.POINTER(Stats)]),
         "drt_render": (C.c_int, [vp, vp, C.POINTER(Stats)]),
@@ -107,7 +110,7 @@ def load_library():
 
 EXPORTS = ["drt_create", "drt_destroy", "drt_last_error", "drt_set_image_loader", "drt_set_texture_dir", "drt_scene_reset",
            "drt_scene_command", "drt_scene_load_cli", "drt_scene_override", "drt_scene_finalize", "drt_scene_reupload",
-           "drt_scene_info", "drt_scene_counts", "drt_build_info", "drt_bvh_order", "drt_lbvh_probe", "drt_accel_info", "drt_emit_photons", "drt_render", "drt_render_aov", "drt_render_device", "drt_render_device_chunks", "drt_save_png",
+           "drt_scene_info", "drt_scene_counts", "drt_build_info", "drt_bvh_order", "drt_lbvh_probe", "drt_scene_refine", "drt_refine_steps", "drt_refine_pass", "drt_accel_info", "drt_emit_photons", "drt_render", "drt_render_aov", "drt_render_device", "drt_render_device_chunks", "drt_save_png",
            "drt_trace_rays", "drt_eval_texture", "drt_dump_bvh", "drt_obj_ctm", "drt_sample_u01", "drt_get_photons",
            "drt_emit_photons_range", "drt_photons_export_device", "drt_photons_build_device", "drt_photon_probe",
            "drt_comm_unique_id", "drt_comm_init", "drt_comm_destroy", "drt_render_distributed",
@@ -191,6 +194,22 @@ class Context:
             pass
 
 
+def refine_steps(cols, rows):
+    """Step sequence of the reference's progressive refinement display for a cols x rows frame (myScene.setRefine)."""
+    o = (C.c_int32 * 16)()
+    n = load_library().drt_refine_steps(cols, rows, o)
+    return [int(o[i]) for i in range(n)]
+
+
+def refine_pass(argb_full, step):
+    """Preview of one refinement step, made from the finished frame (rows x cols ARGB ints)."""
+    a = np.ascontiguousarray(argb_full, dtype=np.int32)
+    out = np.empty_like(a)
+    if load_library().drt_refine_pass(a.ctypes.data, a.shape[1], a.shape[0], step, out.ctypes.data) != 0:
+        raise DrtError("drt_refine_pass: bad arguments")
+    return out
+
+
 class Scene:
     """Mirror of the reference's myScene for the render path."""
 
@@ -233,6 +252,10 @@ class Scene:
         o = (C.c_int64 * 8)()
         self.ctx._ck(self.L.drt_scene_counts(self.ctx.h, o))
         return {"tris_packed": o[0], "fast_bvhs": o[1], "top_tris_packed": o[2], "tris_in_fast_bvhs": o[3], "children": o[4], "pdata_doubles": o[5]}
+
+    def refine_on(self):
+        """`refine on` was set by the scene (myScene.setRefine)."""
+        return self.L.drt_scene_refine(self.ctx.h) == 1
 
     def build_info(self):
         o = (C.c_double * 8)()

@@ -113,6 +113,16 @@ int64_t drt_dist_rank_pixels(int32_t cols, int32_t rows, int32_t world, int32_t 
 int64_t drt_dist_abs_pixel(int32_t cols, int32_t rows, int32_t world, int32_t rank, int32_t chunk_rows, int64_t compact_index);
 int drt_dist_photon_range(int64_t n_cast, int32_t world, int32_t rank, int64_t* out2);
 int drt_save_png(const char* path, const int32_t* argb, int32_t cols, int32_t rows);  /* PImage.save (myScene.java:1194) */
+/* ---- progressive refinement display (`refine on`: myScene.setRefine :796-803, the pass loop of draw() :1493-1526, writePxlSpan :1171-1177).
+ * The reference shows a sequence of previews: pass k traces every step_k-th pixel of every step_k-th row (step = 2^refIDX ... 2, 1 with
+ * refIDX = (int)(log10(.5 (cols + rows) / 16) / log10(2))) and paints each result over a step x step block.  It re-traces the pixels on every
+ * pass; with this library's seeded sampler a pixel's colour does not depend on the pass, so every preview is a function of the finished frame:
+ * block (r, c) shows the frame's pixel at the block's top-left corner.  drt_scene_refine: 1 when the scene said `refine on`;
+ * drt_refine_steps: the step sequence (returns its length, 0 when the reference's formula yields none: frames smaller than 16 pixels mean size);
+ * drt_refine_pass: the preview of one step from the finished frame (pure host functions: the frame itself comes from drt_render). */
+int drt_scene_refine(drt_ctx* ctx);
+int32_t drt_refine_steps(int32_t cols, int32_t rows, int32_t* steps16);
+int drt_refine_pass(const int32_t* argb_full, int32_t cols, int32_t rows, int32_t step, int32_t* argb_out);
 
 /* ---- parity probes (used by tests; not needed by a host) ---- */
 int drt_trace_rays(drt_ctx* ctx, int64_t n, const double* org, const double* dir, int32_t* ids2, double* t);

@@ -221,3 +221,36 @@ def test_build_probes_on_a_host_only_context(drt):
     with pytest.raises(drt.DrtError):
         ctx.bvh_order(keys, on_device=True)
     ctx.close()
+
+
+def test_progressive_refinement_previews_match_the_reference_pass_loop(drt):
+    """`refine on` (myScene.setRefine :796-803; draw() :1493-1526; writePxlSpan :1171-1177).  A literal Python restatement of the reference's
+    pass loop -- every pass re-"traces" its pixels (here: looks them up in a finished frame, which is what a seeded sampler makes them), skips pixel
+    (0, 0) on all passes but the first and paints step x step spans into the persistent image -- against drt_refine_steps / drt_refine_pass."""
+    import math
+    rng = np.random.default_rng(4)
+    for cols, rows in ((300, 300), (317, 203), (64, 48), (3840, 2160)):
+        ref_idx = int(math.log10(.5 * (cols + rows) / 16.0) / math.log10(2.0))
+        want_steps = [2 ** i for i in range(ref_idx, -1, -1)]
+        assert drt.refine_steps(cols, rows) == want_steps
+        if cols > 1000:
+            continue
+        full = rng.integers(-2 ** 31, 2 ** 31 - 1, size=(rows, cols), dtype=np.int64).astype(np.int32)
+        img = np.zeros((rows, cols), dtype=np.int32)                       # rndrdImg.pixels persists across the passes
+        for k, step in enumerate(want_steps):
+            skip = k != 0
+            for row in range(0, rows, step):
+                for col in range(0, cols, step):
+                    if skip:
+                        skip = False
+                        continue
+                    img[row:min(row + step, rows), col:min(col + step, cols)] = full[row, col]
+            assert np.array_equal(drt.refine_pass(full, step), img), (cols, rows, step)
+        assert np.array_equal(img, full)
+    assert drt.refine_steps(8, 8) == []                                     # the reference's formula yields no pass (negative array size there)
+    ctx = drt.Context(device=-1)
+    sc = drt.Scene(ctx)
+    assert not sc.refine_on()
+    sc.command("refine on"); assert sc.refine_on()
+    sc.command("refine off"); assert not sc.refine_on()
+    ctx.close()
