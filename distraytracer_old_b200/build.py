@@ -58,7 +58,9 @@ def kernel_hash(refresh=False):
     r = subprocess.run([cuobjdump, "-sass", LIB], capture_output=True)
     if r.returncode != 0:
         return "unknown"
-    h = hashlib.sha1(r.stdout).hexdigest()[:16]
+    # instruction and function-name lines only: the dump also carries the absolute path of the source file ("identifier = ..."), which must not matter
+    body = b"\n".join(l for l in r.stdout.split(b"\n") if l.lstrip().startswith((b"/*", b"Function :")))
+    h = hashlib.sha1(body).hexdigest()[:16]
     open(HASH_FILE, "w").write(h + "\n")
     return h
 
